@@ -1,0 +1,106 @@
+/*
+ * sorobn_b200 -- C ABI of the B200 exact-inference engine.
+ *
+ * This is the drop-in boundary for the exact-inference path of MaxHalford/sorobn.
+ * The reference has no native layer: the whole path is Python over pandas
+ * (/root/reference/sorobn/bayes_net.py).  The entry points below are what a ctypes
+ * binding inside the reference's `BayesNet` would call instead of
+ *
+ *   - `BayesNet._variable_elimination`      bayes_net.py:739-794  (the loop)
+ *   - `pointwise_mul` / `pointwise_mul_two` bayes_net.py:106-256  (factor product)
+ *   - `CDTAccessor.sum_out`                 bayes_net.py:54-103   (marginalisation)
+ *   - the normalisation at                  bayes_net.py:789-790
+ *
+ * INTEGRATION.md shows that binding.  Plain pointers and sizes only: no torch,
+ * numpy or pandas types cross this line.
+ *
+ * A *program* is the frozen form of one `(query variables, evidence variables)`
+ * pair: the CPTs involved (dense fp32 tables) and the list of fused
+ * "product of k factors -> sum out one variable" steps, one kernel launch each
+ * (word layout: sorobn_b200/planner.py).  Running a program on B evidence rows
+ * computes B posteriors, i.e. B calls of `BayesNet.query(..., algorithm="exact")`.
+ *
+ * Layouts (both "column-major" over rows so that device accesses coalesce):
+ *   evidence : uint8 state codes, ev[c * ld_ev + b]   c < n_ev, b < n_rows
+ *   posterior: float,             out[q * ld_out + b] q < Q,    b < n_rows
+ * where q enumerates the joint states of the query variables, variables sorted by
+ * name and the last one varying fastest -- the row order of the reference's answer
+ * (`reorder_levels(sorted(...))`, `sort_index()`; bayes_net.py:872-875).
+ * A row whose evidence has probability zero yields NaN (the reference returns an
+ * empty Series there).
+ *
+ * Every function returns 0 on success or a negative SBN_E_* code;
+ * sbn_last_error() then describes the failure (thread-local string).
+ */
+#ifndef SOROBN_B200_H
+#define SOROBN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBN_ABI_VERSION 2
+
+#define SBN_OK 0
+#define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
+#define SBN_E_CUDA (-2)      /* CUDA runtime error (see sbn_last_error)     */
+#define SBN_E_NOMEM (-3)     /* scratch does not fit the device             */
+#define SBN_E_NODEVICE (-4)  /* no usable sm_100 GPU                        */
+
+typedef struct sbn_program sbn_program;
+
+/* Fixed limits of the step kernel (also enforced by the planner). */
+#define SBN_MAX_IN 8     /* factors multiplied in one launch   */
+#define SBN_MAX_AXES 20  /* variables in one output factor     */
+#define SBN_MAX_EV 8     /* evidence axes gathered per factor  */
+
+int sbn_abi_version(void);
+const char *sbn_last_error(void);
+
+/* Number of CUDA devices visible; SBN_E_NODEVICE if none. */
+int sbn_device_count(int *count);
+
+/* Compile a program for `device`: validates `words` (planner.py layout), uploads the
+ * CPT tables.  Replaces the per-query factor preparation of bayes_net.py:768-776. */
+int sbn_program_create(int device, const int32_t *words, int64_t n_words, const float *tables,
+                       int64_t n_table_floats, sbn_program **out);
+void sbn_program_destroy(sbn_program *prog);
+
+/* Allocate scratch for chunks of up to `max_rows` evidence rows (larger batches are
+ * processed in chunks).  Called implicitly by the run functions when needed. */
+int sbn_program_reserve(sbn_program *prog, int64_t max_rows);
+
+/* Answer `n_rows` queries with HOST buffers: copies the evidence codes to the device,
+ * runs every step, copies the posteriors back and synchronises.  This is the call that
+ * replaces `BayesNet._variable_elimination` (bayes_net.py:739) for a batch of events. */
+int sbn_program_run_host(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out,
+                         int64_t ld_out);
+
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = default
+ * stream).  n_rows must not exceed the reserved chunk size. */
+int sbn_program_run_device(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                           int64_t ld_out, void *stream);
+
+/* Per-step device time of one run on device buffers (CUDA events around every launch;
+ * diagnostic, not the fast path).  step_ms has n_steps + 1 entries (last = normalise). */
+int sbn_program_profile(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                        int64_t ld_out, void *stream, float *step_ms, int64_t n_step_ms);
+
+/* info[0]=Q  [1]=n_ev  [2]=n_steps  [3]=scratch floats per row  [4]=reserved rows
+ * [5]=kernel launches issued by this program so far  [6]=mode (0 flat, 1 batched)
+ * [7]=unbatched scratch floats */
+int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
+
+/* Toggle CUDA-graph replay of the step sequence (default on). */
+int sbn_program_set_graph(sbn_program *prog, int enabled);
+
+/* Pinned host memory for evidence / posterior staging buffers. */
+int sbn_host_alloc(void **ptr, int64_t bytes);
+int sbn_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOROBN_B200_H */

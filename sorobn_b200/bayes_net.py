@@ -1,0 +1,317 @@
+"""Host-side mirror of `sorobn.BayesNet` for the exact-inference path.
+
+Same surface as the reference (/root/reference/sorobn/bayes_net.py:259-1075) for
+everything on the hot path: the constructor's structure grammar, the `P` dict of
+pandas Series, `prepare()`, `query(..., algorithm="exact")` and `impute()`, plus the
+cheap structural helpers.  What differs is where the arithmetic runs: `prepare()`
+additionally compiles the CPTs into dense fp32 tables, and `query()` hands a flat
+variable-elimination program to the CUDA engine (`sorobn_b200.engine`, a ctypes
+shim over `libsorobn_b200.so`).  There is no CPU fallback: without the CUDA library
+or a GPU `query()` raises.
+
+`query_many()` is the batched form of `query()` (one posterior per evidence row of a
+DataFrame); it is what the multi-GPU sharding and the benchmark drive.
+
+The sampling-based algorithms (gibbs / likelihood / rejection, bayes_net.py:577-737)
+and `fit` / `partial_fit` / `sample` are outside this path (scope table).
+"""
+from __future__ import annotations
+
+import graphlib
+from collections import defaultdict
+
+import numpy as np
+import pandas as pd
+
+from . import planner as _planner
+
+__all__ = ["BayesNet"]
+
+
+def _as_list(obj):
+    return obj if isinstance(obj, list) else [obj]
+
+
+class BayesNet:
+    """Bayesian network with CUDA exact inference.
+
+    Parameters mirror bayes_net.py:286: `structure` items are either bare nodes or
+    (parent(s), child(ren)) tuples whose members may be lists.
+    """
+
+    def __init__(self, *structure, prior_count: int = None, seed: int = None, device: int | None = None):
+        self.prior_count = prior_count
+        self.seed = seed
+        self.device = device
+
+        parents = defaultdict(set)
+        children = defaultdict(set)
+        lone = set()
+        for item in structure:
+            if isinstance(item, tuple):
+                srcs, dsts = item
+                for s in _as_list(srcs):
+                    for d in _as_list(dsts):
+                        parents[d].add(s)
+                        children[s].add(d)
+            else:
+                lone.add(item)
+
+        # bayes_net.py:312-315: plain dicts of sorted lists
+        self.parents = {n: sorted(ps) for n, ps in parents.items()}
+        self.children = {n: sorted(cs) for n, cs in children.items()}
+
+        # bayes_net.py:317-322: topological order, lexicographic within a level.
+        # graphlib raises CycleError for a cyclic structure, as the reference does.
+        sorter = graphlib.TopologicalSorter()
+        for n in sorted({*self.parents, *self.children, *lone}):
+            sorter.add(n, *self.parents.get(n, []))
+        self.nodes = list(sorter.static_order())
+
+        self.P = {}
+        self._P_sizes = {}
+        self._compiled = None
+        self._engine_cache = {}
+
+    # ------------------------------------------------------------------ structure
+    def ancestors(self, node):
+        """bayes_net.py:373-378."""
+        found = set()
+        frontier = list(self.parents.get(node, ()))
+        while frontier:
+            p = frontier.pop()
+            if p not in found:
+                found.add(p)
+                frontier.extend(self.parents.get(p, ()))
+        return found
+
+    @property
+    def roots(self):
+        return [n for n in self.nodes if n not in self.parents]
+
+    @property
+    def leaves(self):
+        return [n for n in self.nodes if n not in self.children]
+
+    @property
+    def is_tree(self):
+        return all(len(ps) <= 1 for ps in self.parents.values())
+
+    def markov_boundary(self, node):
+        """Parents, children and the children's other parents (bayes_net.py:1002-1039)."""
+        kids = self.children.get(node, [])
+        blanket = set(self.parents.get(node, [])) | set(kids)
+        for k in kids:
+            blanket |= set(self.parents[k])
+        blanket.discard(node)
+        return sorted(blanket)
+
+    def iter_dfs(self):
+        """Depth-first walk from each root (bayes_net.py:1041-1075)."""
+        seen = set()
+
+        def walk(n):
+            yield n
+            seen.add(n)
+            for c in self.children.get(n, []):
+                if c not in seen:
+                    yield from walk(c)
+
+        for r in self.roots:
+            yield from walk(r)
+
+    # -------------------------------------------------------------------- prepare
+    def prepare(self) -> "BayesNet":
+        """House-keeping (bayes_net.py:327-371) + compile the tables for the device.
+
+        The pandas side ends in the same state as the reference's: each `P[node]` is
+        a Series named "P(node | parents)" whose index levels are
+        [*parents, node], sorted.  Then every CPT is densified into an fp32 table
+        (domain order == the sorted level values) ready to be shipped.
+        """
+        for node in list(self.P):
+            table = self.P[node]
+            node_parents = self.parents.get(node, [])
+
+            if isinstance(table, pd.DataFrame):
+                # bayes_net.py:339-358
+                if "p" not in table.columns:
+                    raise ValueError(
+                        f"DataFrame for '{node}' must have a 'p' column containing probabilities"
+                    )
+                given = [c for c in table.columns if c != "p"]
+                wanted = set(node_parents) | {node}
+                if set(given) != wanted:
+                    raise ValueError(
+                        f"DataFrame for '{node}' has columns {given}, but expected {sorted(wanted)} (plus 'p')"
+                    )
+                table = table.set_index([*node_parents, node])["p"]
+                self.P[node] = table
+
+            if node not in self.parents:
+                table.index.name = node
+            elif set(table.index.names) == {*node_parents, node}:
+                table = table.reorder_levels([*node_parents, node])
+            else:
+                table.index.names = [*node_parents, node]
+            # reorder_levels returns a new object: sort it and store it back so that
+            # P[node] always carries [*parents, node] levels, sorted
+            table = table.sort_index()
+            table.name = (
+                f"P({node} | {', '.join(map(str, node_parents))})" if node in self.parents else f"P({node})"
+            )
+            self.P[node] = table
+
+        self._compile()
+        return self
+
+    def _compile(self):
+        missing = [n for n in self.nodes if n not in self.P]
+        if missing:
+            # The reference tolerates a partially specified network until a query
+            # touches the hole; keep that: compile lazily once everything is there.
+            self._compiled = None
+            self._engine_cache = {}
+            return
+        seen = {n: set() for n in self.nodes}
+        for node, series in self.P.items():
+            idx = series.index
+            if isinstance(idx, pd.MultiIndex):
+                for lvl, name in enumerate(idx.names):
+                    seen[name].update(idx.get_level_values(lvl).unique().tolist())
+            else:
+                seen[node].update(idx.unique().tolist())
+        domains = {n: sorted(v) for n, v in seen.items()}
+        vid = {n: i for i, n in enumerate(self.nodes)}
+        cpts = []
+        for node in self.nodes:
+            scope = [*self.parents.get(node, []), node]
+            series = self.P[node]
+            shape = [len(domains[v]) for v in scope]
+            dense = np.zeros(shape, dtype=np.float64)
+            idx = series.index
+            if isinstance(idx, pd.MultiIndex):
+                codes = [pd.Index(domains[v]).get_indexer(idx.get_level_values(l)) for l, v in enumerate(scope)]
+            else:
+                codes = [pd.Index(domains[node]).get_indexer(idx)]
+            dense[tuple(codes)] = series.to_numpy(dtype=np.float64)
+            cpts.append(dense)
+        self._compiled = _planner.CompiledNet(
+            names=list(self.nodes),
+            domains=[domains[n] for n in self.nodes],
+            parents=[[vid[p] for p in self.parents.get(n, [])] for n in self.nodes],
+            cpt=cpts,
+        )
+        self._engine_cache = {}
+
+    # ---------------------------------------------------------------------- query
+    def _plan(self, query, evidence_vars, mode):
+        if self._compiled is None:
+            self._compile()
+            if self._compiled is None:
+                raise ValueError("every node needs a CPT in P before querying; call prepare()")
+        net = self._compiled
+        key = (tuple(query), tuple(evidence_vars), mode)
+        hit = self._engine_cache.get(key)
+        if hit is None:
+            for name in (*query, *evidence_vars):
+                if name not in net.index:
+                    raise KeyError(name)
+            plan = _planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evidence_vars],
+                                       mode=mode)
+            from . import engine  # raises if libsorobn_b200.so cannot be loaded
+
+            hit = (plan, engine.Program(plan, device=self.device))
+            self._engine_cache[key] = hit
+        return hit
+
+    def _encode_events(self, evidence_vars, columns):
+        """State values -> uint8 codes [n_ev, B].  Unknown values get code 255 and the
+        row is reported as impossible evidence (the reference's boolean filter at
+        bayes_net.py:772-774 leaves an empty factor, hence an empty answer)."""
+        net = self._compiled
+        n = len(columns[0]) if columns else 0
+        codes = np.empty((len(evidence_vars), n), dtype=np.uint8)
+        bad = np.zeros(n, dtype=bool)
+        for i, (name, col) in enumerate(zip(evidence_vars, columns)):
+            dom = pd.Index(net.domains[net.index[name]])
+            c = dom.get_indexer(pd.Index(col))
+            bad |= c < 0
+            codes[i] = np.where(c < 0, 0, c).astype(np.uint8)
+        return codes, bad
+
+    def _answer_index(self, plan):
+        net = self._compiled
+        names = [net.names[v] for v in plan.query]
+        doms = [net.domains[v] for v in plan.query]
+        if len(names) == 1:
+            return pd.Index(doms[0], name=names[0])
+        return pd.MultiIndex.from_product(doms, names=names)
+
+    def query(self, *query, event: dict, algorithm="exact", n_iterations=100) -> pd.Series:
+        """Answer P(query | event) (bayes_net.py:796-875), exact inference on the GPU.
+
+        The answer is a Series named "P(q1, q2)" indexed by the query variables
+        (levels sorted by name, rows sorted by state); states with zero posterior
+        are left out, as the reference's zero-filtering join does
+        (bayes_net.py:253-256).
+        """
+        if not query:
+            raise ValueError("At least one query variable has to be specified")
+        for q in query:
+            if q in event:
+                raise ValueError("A query variable cannot be part of the event")
+        if algorithm != "exact":
+            if algorithm in ("gibbs", "likelihood", "rejection"):
+                raise NotImplementedError(
+                    f"algorithm={algorithm!r} is outside the CUDA exact-inference path (see DESIGN.md)"
+                )
+            raise ValueError("Unknown algorithm, must be one of: exact, gibbs, likelihood, rejection")
+
+        ev_vars = tuple(event)
+        plan, program = self._plan(query, ev_vars, _planner.MODE_FLAT)
+        codes, bad = self._encode_events(ev_vars, [[event[v]] for v in ev_vars])
+        index = self._answer_index(plan)
+        name = f"P({', '.join(map(str, query))})"
+        if bad.any():
+            return pd.Series([], index=index[:0], name=name, dtype=np.float64)
+        post = program.run(codes, 1)[:, 0].astype(np.float64)
+        answer = pd.Series(post, index=index, name=name)
+        if np.isnan(post).any():  # impossible evidence: P(event) == 0
+            return answer.iloc[:0]
+        return answer[post > 0]
+
+    def query_many(self, *query, events: pd.DataFrame, algorithm="exact") -> pd.DataFrame:
+        """Batched `query`: one posterior per row of `events` (columns = evidence
+        variables).  Returns a DataFrame with one row per evidence row and one column
+        per joint state of the query variables (same order as `query`'s index);
+        impossible rows are NaN.  Zero-probability states stay (as 0.0)."""
+        if not query:
+            raise ValueError("At least one query variable has to be specified")
+        ev_vars = tuple(events.columns)
+        for q in query:
+            if q in ev_vars:
+                raise ValueError("A query variable cannot be part of the event")
+        if algorithm != "exact":
+            raise NotImplementedError("query_many only implements algorithm='exact'")
+        plan, program = self._plan(query, ev_vars, _planner.MODE_BATCHED)
+        codes, bad = self._encode_events(ev_vars, [events[v].to_numpy() for v in ev_vars])
+        n = len(events)
+        post = program.run(codes, n)  # [Q, n]
+        out = pd.DataFrame(post.T.astype(np.float64), index=events.index, columns=self._answer_index(plan))
+        if bad.any():
+            out.loc[events.index[bad]] = np.nan
+        return out
+
+    def impute(self, sample: dict, **query_params) -> pd.Series:
+        """Fill the `None` entries of `sample` with their most probable joint value
+        (bayes_net.py:877-908)."""
+        known = {k: v for k, v in sample.items() if v is not None}
+        unknown = [k for k, v in sample.items() if v is None]
+        posterior = self.query(*unknown, event=known, **query_params)
+        best = posterior.idxmax()
+        if not isinstance(best, tuple):
+            best = (best,)
+        for k, v in zip(posterior.index.names, best):
+            known[k] = v
+        return pd.Series(known)

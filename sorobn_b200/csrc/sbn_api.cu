@@ -1,0 +1,687 @@
+// sorobn_b200 -- C-ABI engine: program parsing, scratch management, launches.
+//
+// Host-side counterpart of `BayesNet._variable_elimination`
+// (/root/reference/sorobn/bayes_net.py:739-794): the reference walks the hidden
+// variables in Python and calls pandas for every product / sum-out; here the walk was
+// frozen by sorobn_b200/planner.py into a list of steps and this file replays it as
+// kernel launches (optionally captured in a CUDA graph) for a batch of evidence rows.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sbn_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define SBN_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(SBN_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                  \
+    } while (0)
+
+constexpr int32_t kMagic = 0x53424E31;
+constexpr int kVersion = 3;
+constexpr int kHeaderWords = 12;
+
+struct EvAxis {
+    int col, stride, card;
+};
+struct InDesc {
+    bool is_slot;
+    int id;
+    bool batched;
+    int sx;
+    std::vector<EvAxis> ev;
+    std::vector<int> strides;
+};
+struct StepDesc {
+    int kind;
+    int out_slot;
+    int cx;
+    int64_t n_out;
+    std::vector<int> cards;
+    std::vector<InDesc> in;
+};
+struct Slot {
+    bool batched;
+    int64_t size;     // floats per row (batched) or in total
+    int64_t padded;   // size rounded up to 4 floats (bulk-TMA granularity)
+    float *ptr;
+};
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct sbn_program {
+    int device = 0;
+    int mode = 0, n_ev = 0, Q = 0, post_slot = 0, post_batched = 0;
+    std::vector<std::pair<int64_t, int64_t>> tables;  // (offset, size) in floats
+    std::vector<int64_t> table_padded;
+    float *d_tables = nullptr;
+    std::vector<Slot> slots;
+    std::vector<StepDesc> steps;
+
+    int64_t reserved_rows = 0;  // chunk capacity
+    int64_t ld = 0;             // row pitch of batched scratch (floats)
+    float *d_arena = nullptr;   // batched scratch
+    float *d_shared = nullptr;  // unbatched scratch
+    uint8_t *d_ev = nullptr;    // staging for run_host  [n_ev][ld]
+    float *d_out = nullptr;     //                         [Q][ld]
+    cudaStream_t stream = nullptr;
+
+    bool use_graph = true;
+    cudaGraphExec_t exec = nullptr;
+    struct {
+        const uint8_t *ev;
+        int64_t ld_ev, n_rows;
+        float *out;
+        int64_t ld_out;
+    } graph_key = {nullptr, 0, 0, nullptr, 0};
+    int64_t graph_launches = 0;
+
+    int64_t launches = 0;
+    int max_dyn_smem_set = 0;
+};
+
+namespace {
+
+int parse(sbn_program *P, const int32_t *w, int64_t n) {
+    if (n < kHeaderWords) return fail(SBN_E_INVALID, "program shorter than its header");
+    if (w[0] != kMagic) return fail(SBN_E_INVALID, "bad program magic 0x%x", w[0]);
+    if (w[1] != kVersion) return fail(SBN_E_INVALID, "program version %d, engine expects %d", w[1], kVersion);
+    P->mode = w[2];
+    P->n_ev = w[3];
+    const int n_tables = w[4], n_slots = w[5], n_steps = w[6];
+    P->Q = w[7];
+    P->post_slot = w[8];
+    P->post_batched = w[9];
+    if (P->mode != 0 && P->mode != 1) return fail(SBN_E_INVALID, "bad mode %d", P->mode);
+    if (P->n_ev < 0 || n_tables < 0 || n_slots <= 0 || n_steps <= 0 || P->Q <= 0)
+        return fail(SBN_E_INVALID, "bad header counts");
+    if (P->post_slot < 0 || P->post_slot >= n_slots) return fail(SBN_E_INVALID, "post slot out of range");
+    int64_t p = kHeaderWords;
+    auto need = [&](int64_t k) { return p + k <= n; };
+    if (!need(2LL * n_tables + 2LL * n_slots)) return fail(SBN_E_INVALID, "truncated table/slot section");
+    for (int t = 0; t < n_tables; ++t) {
+        const int64_t off = w[p], size = w[p + 1];
+        p += 2;
+        if (off < 0 || size <= 0 || (off % 4) != 0) return fail(SBN_E_INVALID, "bad table %d", t);
+        P->tables.push_back({off, size});
+        P->table_padded.push_back(round_up(size, 4));
+    }
+    for (int s = 0; s < n_slots; ++s) {
+        const int batched = w[p];
+        const int64_t size = w[p + 1];
+        p += 2;
+        if ((batched != 0 && batched != 1) || size <= 0) return fail(SBN_E_INVALID, "bad slot %d", s);
+        if (batched && P->mode == 0) return fail(SBN_E_INVALID, "batched slot in a flat program");
+        P->slots.push_back({batched != 0, size, round_up(size, 4), nullptr});
+    }
+    if ((P->slots[P->post_slot].batched ? 1 : 0) != P->post_batched || P->slots[P->post_slot].size < P->Q)
+        return fail(SBN_E_INVALID, "posterior slot mismatch");
+    for (int s = 0; s < n_steps; ++s) {
+        if (!need(5)) return fail(SBN_E_INVALID, "truncated step %d", s);
+        StepDesc st;
+        st.kind = w[p];
+        const int n_in = w[p + 1];
+        st.out_slot = w[p + 2];
+        const int n_axes = w[p + 3];
+        st.cx = w[p + 4];
+        p += 5;
+        if (st.kind != 0 && st.kind != 1) return fail(SBN_E_INVALID, "step %d: bad kind", s);
+        if (st.kind == 1 && P->mode == 0) return fail(SBN_E_INVALID, "step %d: batched step in a flat program", s);
+        if (n_in < 1 || n_in > SBN_MAX_IN) return fail(SBN_E_INVALID, "step %d: %d inputs", s, n_in);
+        if (n_axes < 0 || n_axes > SBN_MAX_AXES) return fail(SBN_E_INVALID, "step %d: %d axes", s, n_axes);
+        if (st.cx < 1) return fail(SBN_E_INVALID, "step %d: cx %d", s, st.cx);
+        if (st.out_slot < 0 || st.out_slot >= n_slots) return fail(SBN_E_INVALID, "step %d: out slot", s);
+        if (!need(n_axes)) return fail(SBN_E_INVALID, "truncated step %d", s);
+        st.n_out = 1;
+        for (int j = 0; j < n_axes; ++j) {
+            const int c = w[p + j];
+            if (c < 1) return fail(SBN_E_INVALID, "step %d: axis card %d", s, c);
+            st.n_out *= c;
+            if (st.n_out >= (1LL << 31)) return fail(SBN_E_INVALID, "step %d: output too large", s);
+            st.cards.push_back(c);
+        }
+        p += n_axes;
+        const Slot &os = P->slots[st.out_slot];
+        if (os.batched != (st.kind == 1)) return fail(SBN_E_INVALID, "step %d: out slot kind mismatch", s);
+        if (os.size < st.n_out) return fail(SBN_E_INVALID, "step %d: out slot too small", s);
+        for (int i = 0; i < n_in; ++i) {
+            if (!need(5)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
+            InDesc in;
+            in.is_slot = w[p] != 0;
+            in.id = w[p + 1];
+            in.batched = w[p + 2] != 0;
+            in.sx = w[p + 3];
+            const int n_ev = w[p + 4];
+            p += 5;
+            if (n_ev < 0 || n_ev > SBN_MAX_EV) return fail(SBN_E_INVALID, "step %d input %d: %d ev axes", s, i, n_ev);
+            if (!need(3LL * n_ev + n_axes)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
+            int64_t size;
+            if (in.is_slot) {
+                if (in.id < 0 || in.id >= n_slots) return fail(SBN_E_INVALID, "step %d input %d: slot id", s, i);
+                if (in.id == st.out_slot) return fail(SBN_E_INVALID, "step %d: output aliases input %d", s, i);
+                if (P->slots[in.id].batched != in.batched)
+                    return fail(SBN_E_INVALID, "step %d input %d: batched flag mismatch", s, i);
+                size = P->slots[in.id].size;
+            } else {
+                if (in.id < 0 || in.id >= n_tables) return fail(SBN_E_INVALID, "step %d input %d: table id", s, i);
+                if (in.batched) return fail(SBN_E_INVALID, "step %d input %d: batched table", s, i);
+                size = P->tables[in.id].second;
+            }
+            if (in.batched && st.kind != 1) return fail(SBN_E_INVALID, "step %d: batched input in flat step", s);
+            if (in.batched && n_ev) return fail(SBN_E_INVALID, "step %d input %d: batched input with ev axes", s, i);
+            if (n_ev && st.kind != 1 && P->mode != 0)
+                return fail(SBN_E_INVALID, "step %d input %d: evidence axes in an unbatched step", s, i);
+            if (in.sx < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
+            int64_t max_off = static_cast<int64_t>(st.cx - 1) * in.sx;
+            for (int k = 0; k < n_ev; ++k) {
+                EvAxis a{w[p], w[p + 1], w[p + 2]};
+                p += 3;
+                if (a.col < 0 || a.col >= P->n_ev || a.stride < 0 || a.card < 1 || a.card > 256)
+                    return fail(SBN_E_INVALID, "step %d input %d: bad ev axis", s, i);
+                max_off += static_cast<int64_t>(a.card - 1) * a.stride;
+                in.ev.push_back(a);
+            }
+            for (int j = 0; j < n_axes; ++j) {
+                const int sj = w[p + j];
+                if (sj < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
+                max_off += static_cast<int64_t>(st.cards[j] - 1) * sj;
+                in.strides.push_back(sj);
+            }
+            p += n_axes;
+            if (max_off >= size) return fail(SBN_E_INVALID, "step %d input %d: reads past its buffer", s, i);
+            st.in.push_back(std::move(in));
+        }
+        P->steps.push_back(std::move(st));
+    }
+    if (p != n) return fail(SBN_E_INVALID, "trailing words in program");
+    if (P->steps.back().out_slot != P->post_slot) return fail(SBN_E_INVALID, "last step does not write the posterior");
+    return SBN_OK;
+}
+
+void free_scratch(sbn_program *P) {
+    if (P->exec) {
+        cudaGraphExecDestroy(P->exec);
+        P->exec = nullptr;
+    }
+    cudaFree(P->d_arena);
+    cudaFree(P->d_ev);
+    cudaFree(P->d_out);
+    P->d_arena = nullptr;
+    P->d_ev = nullptr;
+    P->d_out = nullptr;
+    P->reserved_rows = 0;
+    P->ld = 0;
+}
+
+int64_t batched_floats_per_row(const sbn_program *P) {
+    int64_t t = 0;
+    for (const Slot &s : P->slots)
+        if (s.batched) t += s.size;
+    return t;
+}
+
+// Fill the kernel parameter block of one step.
+void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, int64_t ld_ev, int64_t n_rows,
+                  SbnStep *q) {
+    memset(q, 0, sizeof *q);
+    q->out = P->slots[st.out_slot].ptr;
+    q->ev = ev;
+    q->ld_ev = ld_ev;
+    q->ld = P->ld;
+    q->n_rows = static_cast<int32_t>(n_rows);
+    q->n_in = static_cast<int32_t>(st.in.size());
+    q->n_axes = static_cast<int32_t>(st.cards.size());
+    q->cx = st.cx;
+    q->n_out = static_cast<int32_t>(st.n_out);
+    for (size_t j = 0; j < st.cards.size(); ++j) q->card[j] = st.cards[j];
+    int smem = 0;
+    for (size_t i = 0; i < st.in.size(); ++i) {
+        const InDesc &in = st.in[i];
+        SbnInput &d = q->in[i];
+        int64_t padded;
+        if (in.is_slot) {
+            d.ptr = P->slots[in.id].ptr;
+            padded = P->slots[in.id].padded;
+        } else {
+            d.ptr = P->d_tables + P->tables[in.id].first;
+            padded = P->table_padded[in.id];
+        }
+        d.batched = in.batched ? 1 : 0;
+        d.sx = in.sx;
+        d.n_ev = static_cast<int32_t>(in.ev.size());
+        for (size_t k = 0; k < in.ev.size(); ++k) {
+            d.ev_col[k] = in.ev[k].col;
+            d.ev_stride[k] = in.ev[k].stride;
+            d.ev_card[k] = in.ev[k].card;
+        }
+        for (size_t j = 0; j < in.strides.size(); ++j) d.stride[j] = in.strides[j];
+        d.smem_off = -1;
+        d.stage_floats = 0;
+        if (st.kind == 1 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
+            d.smem_off = smem;
+            d.stage_floats = static_cast<int32_t>(padded);
+            smem += static_cast<int>(padded);
+        }
+    }
+    q->smem_floats = smem;
+    if (st.kind == 1) {
+        const int c0 = q->n_axes > 0 ? q->card[0] : 1;
+        const int c1 = q->n_axes > 1 ? q->card[1] : 1;
+        const int64_t n_bblocks = (n_rows + SBN_ROWS_PER_CTA - 1) / SBN_ROWS_PER_CTA;
+        const int64_t rest = st.n_out / (static_cast<int64_t>(c0) * c1);
+        // Tile = axis 0 x tile1 digits of axis 1.  Start from ~32 outputs per thread and
+        // shrink while the grid is below two full waves (148 SMs x 16 CTAs).
+        int tile1 = std::max(1, std::min(c1, 32 / std::max(1, c0)));
+        auto ctas = [&](int t1) { return n_bblocks * ((c1 + t1 - 1) / t1) * rest; };
+        while (tile1 > 1 && ctas(tile1) < 2 * 148 * 16) tile1 = (tile1 + 1) / 2;
+        q->tile1 = tile1;
+        q->n_tile1 = (c1 + tile1 - 1) / tile1;
+        q->n_bblocks = static_cast<int32_t>(n_bblocks);
+    }
+}
+
+template <int N_IN>
+cudaError_t launch_batched_n(const SbnStep &q, int64_t grid, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
+    const dim3 g(static_cast<unsigned>(grid)), b(SBN_THREADS);
+#define SBN_CASE(CXV)                                                         \
+    case CXV:                                                                 \
+        sbn_step_batched<N_IN, CXV><<<g, b, smem, stream>>>(q);               \
+        break;
+    if constexpr (N_IN <= 4) {
+        switch (q.cx) {
+            SBN_CASE(1)
+            SBN_CASE(2)
+            SBN_CASE(3)
+            SBN_CASE(4)
+            SBN_CASE(5)
+            SBN_CASE(6)
+            SBN_CASE(8)
+            default:
+                sbn_step_batched<N_IN, 0><<<g, b, smem, stream>>>(q);
+        }
+    } else {
+        sbn_step_batched<N_IN, 0><<<g, b, smem, stream>>>(q);
+    }
+#undef SBN_CASE
+    return cudaGetLastError();
+}
+
+template <int N_IN, int CX>
+cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(sbn_step_batched<N_IN, CX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SBN_SMEM_BUDGET);
+}
+template <int N_IN>
+cudaError_t set_smem_attr_n() {
+    cudaError_t e = set_smem_attr<N_IN, 0>();
+    if constexpr (N_IN <= 4) {
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 1>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 2>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 3>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 4>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 5>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 6>();
+        if (e == cudaSuccess) e = set_smem_attr<N_IN, 8>();
+    }
+    return e;
+}
+
+cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cudaStream_t stream) {
+    P->launches++;
+    if (st.kind == 0) {
+        const int threads = 256;
+        const int64_t grid = (st.n_out + threads - 1) / threads;
+        sbn_step_flat<<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
+        return cudaGetLastError();
+    }
+    const int64_t rest = st.n_out / (static_cast<int64_t>(q.n_axes > 0 ? q.card[0] : 1) * (q.n_axes > 1 ? q.card[1] : 1));
+    const int64_t grid = static_cast<int64_t>(q.n_bblocks) * q.n_tile1 * rest;
+    if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
+    switch (q.n_in) {
+        case 1: return launch_batched_n<1>(q, grid, stream);
+        case 2: return launch_batched_n<2>(q, grid, stream);
+        case 3: return launch_batched_n<3>(q, grid, stream);
+        case 4: return launch_batched_n<4>(q, grid, stream);
+        case 5: return launch_batched_n<5>(q, grid, stream);
+        case 6: return launch_batched_n<6>(q, grid, stream);
+        case 7: return launch_batched_n<7>(q, grid, stream);
+        case 8: return launch_batched_n<8>(q, grid, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64_t n_rows, cudaStream_t stream) {
+    P->launches++;
+    const int threads = 256;
+    const int64_t grid = (n_rows + threads - 1) / threads;
+    sbn_normalise<<<static_cast<unsigned>(grid), threads, 0, stream>>>(P->slots[P->post_slot].ptr, P->ld, P->post_batched,
+                                                                     P->Q, d_out, ld_out, static_cast<int>(n_rows));
+    return cudaGetLastError();
+}
+
+int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out, int64_t ld_out,
+              cudaStream_t stream, cudaEvent_t *events) {
+    SbnStep q;
+    int k = 0;
+    for (const StepDesc &st : P->steps) {
+        build_params(P, st, d_ev, ld_ev, n_rows, &q);
+        if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
+        SBN_CUDA(launch_step(P, st, q, stream));
+        ++k;
+    }
+    if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
+    SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, stream));
+    if (events) SBN_CUDA(cudaEventRecord(events[k + 1], stream));
+    return SBN_OK;
+}
+
+int check_run_args(sbn_program *P, const void *ev, int64_t ld_ev, int64_t n_rows, const void *out, int64_t ld_out) {
+    if (!P) return fail(SBN_E_INVALID, "null program");
+    if (n_rows <= 0) return fail(SBN_E_INVALID, "n_rows must be positive");
+    if (!out) return fail(SBN_E_INVALID, "null output");
+    if (P->n_ev > 0 && !ev) return fail(SBN_E_INVALID, "null evidence");
+    if (P->n_ev > 1 && ld_ev < n_rows) return fail(SBN_E_INVALID, "ld_ev < n_rows");
+    if (P->Q > 1 && ld_out < n_rows) return fail(SBN_E_INVALID, "ld_out < n_rows");
+    if (P->mode == 0 && n_rows != 1) return fail(SBN_E_INVALID, "a flat program answers exactly one row");
+    return SBN_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int sbn_abi_version(void) { return SBN_ABI_VERSION; }
+const char *sbn_last_error(void) { return g_err.c_str(); }
+
+int sbn_device_count(int *count) {
+    if (!count) return fail(SBN_E_INVALID, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        *count = 0;
+        return fail(SBN_E_NODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return SBN_OK;
+}
+
+int sbn_program_create(int device, const int32_t *words, int64_t n_words, const float *tables, int64_t n_table_floats,
+                       sbn_program **out) {
+    if (!words || !out || (n_table_floats > 0 && !tables)) return fail(SBN_E_INVALID, "null argument");
+    *out = nullptr;
+    sbn_program *P = new sbn_program();
+    P->device = device;
+    int rc = parse(P, words, n_words);
+    if (rc != SBN_OK) {
+        delete P;
+        return rc;
+    }
+    for (size_t t = 0; t < P->tables.size(); ++t) {
+        if (P->tables[t].first + P->table_padded[t] > n_table_floats) {
+            delete P;
+            return fail(SBN_E_INVALID, "table %zu lies outside the table blob", t);
+        }
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        delete P;
+        return fail(SBN_E_NODEVICE, "no CUDA device available");
+    }
+    if (device < 0 || device >= n_dev) {
+        delete P;
+        return fail(SBN_E_NODEVICE, "device %d out of range (%d visible)", device, n_dev);
+    }
+    auto bail = [&](int code) {
+        sbn_program_destroy(P);
+        return code;
+    };
+#define SBN_CUDA_P(call)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return bail(fail(SBN_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    SBN_CUDA_P(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SBN_CUDA_P(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return bail(fail(SBN_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                                           device, prop.major, prop.minor));
+    SBN_CUDA_P(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    if (n_table_floats > 0) {
+        SBN_CUDA_P(cudaMalloc(&P->d_tables, static_cast<size_t>(n_table_floats) * 4));
+        SBN_CUDA_P(cudaMemcpy(P->d_tables, tables, static_cast<size_t>(n_table_floats) * 4, cudaMemcpyHostToDevice));
+    }
+    // evidence-independent scratch: one allocation, 256-byte aligned sub-buffers
+    int64_t shared_floats = 0;
+    for (Slot &s : P->slots)
+        if (!s.batched) shared_floats += round_up(s.padded, 64);
+    if (shared_floats > 0) {
+        SBN_CUDA_P(cudaMalloc(&P->d_shared, static_cast<size_t>(shared_floats) * 4));
+        SBN_CUDA_P(cudaMemset(P->d_shared, 0, static_cast<size_t>(shared_floats) * 4));
+        int64_t off = 0;
+        for (Slot &s : P->slots)
+            if (!s.batched) {
+                s.ptr = P->d_shared + off;
+                off += round_up(s.padded, 64);
+            }
+    }
+    SBN_CUDA_P(set_smem_attr_n<1>());
+    SBN_CUDA_P(set_smem_attr_n<2>());
+    SBN_CUDA_P(set_smem_attr_n<3>());
+    SBN_CUDA_P(set_smem_attr_n<4>());
+    SBN_CUDA_P(set_smem_attr_n<5>());
+    SBN_CUDA_P(set_smem_attr_n<6>());
+    SBN_CUDA_P(set_smem_attr_n<7>());
+    SBN_CUDA_P(set_smem_attr_n<8>());
+#undef SBN_CUDA_P
+    *out = P;
+    return SBN_OK;
+}
+
+void sbn_program_destroy(sbn_program *P) {
+    if (!P) return;
+    cudaSetDevice(P->device);
+    free_scratch(P);
+    cudaFree(P->d_shared);
+    cudaFree(P->d_tables);
+    if (P->stream) cudaStreamDestroy(P->stream);
+    delete P;
+}
+
+int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
+    if (!P) return fail(SBN_E_INVALID, "null program");
+    if (max_rows <= 0) return fail(SBN_E_INVALID, "max_rows must be positive");
+    if (P->mode == 0) max_rows = 1;
+    if (max_rows <= P->reserved_rows) return SBN_OK;
+    SBN_CUDA(cudaSetDevice(P->device));
+    SBN_CUDA(cudaStreamSynchronize(P->stream));
+    free_scratch(P);
+    const int64_t per_row = batched_floats_per_row(P) * 4 + P->n_ev + static_cast<int64_t>(P->Q) * 4;
+    size_t free_b = 0, total_b = 0;
+    SBN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t budget = static_cast<int64_t>(free_b * 0.85);
+    int64_t rows = max_rows;
+    if (per_row > 0 && round_up(rows, 32) * per_row > budget) rows = (budget / per_row) / 32 * 32;
+    if (rows <= 0)
+        return fail(SBN_E_NOMEM, "one evidence row needs %lld bytes of scratch; %lld free", (long long)per_row,
+                    (long long)free_b);
+    const int64_t ld = round_up(rows, 32);
+    const int64_t arena = batched_floats_per_row(P) * ld;
+    if (arena > 0) {
+        cudaError_t e = cudaMalloc(&P->d_arena, static_cast<size_t>(arena) * 4);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SBN_E_NOMEM, "cudaMalloc of %lld scratch bytes failed: %s", (long long)arena * 4,
+                        cudaGetErrorString(e));
+        }
+        int64_t off = 0;
+        for (Slot &s : P->slots)
+            if (s.batched) {
+                s.ptr = P->d_arena + off;
+                off += s.size * ld;
+            }
+    }
+    if (P->n_ev > 0) {
+        SBN_CUDA(cudaMalloc(&P->d_ev, static_cast<size_t>(P->n_ev) * ld));
+        SBN_CUDA(cudaMemset(P->d_ev, 0, static_cast<size_t>(P->n_ev) * ld));
+    }
+    SBN_CUDA(cudaMalloc(&P->d_out, static_cast<size_t>(P->Q) * ld * 4));
+    P->reserved_rows = rows;
+    P->ld = ld;
+    return SBN_OK;
+}
+
+int sbn_program_run_device(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                           int64_t ld_out, void *stream_) {
+    int rc = check_run_args(P, d_ev, ld_ev, n_rows, d_out, ld_out);
+    if (rc != SBN_OK) return rc;
+    SBN_CUDA(cudaSetDevice(P->device));
+    if (P->reserved_rows == 0) {
+        rc = sbn_program_reserve(P, n_rows);
+        if (rc != SBN_OK) return rc;
+    }
+    if (n_rows > P->reserved_rows)
+        return fail(SBN_E_INVALID, "n_rows %lld exceeds the reserved chunk of %lld rows", (long long)n_rows,
+                    (long long)P->reserved_rows);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!P->use_graph) return issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, stream, nullptr);
+
+    auto &k = P->graph_key;
+    if (!P->exec || k.ev != d_ev || k.ld_ev != ld_ev || k.n_rows != n_rows || k.out != d_out || k.ld_out != ld_out) {
+        if (P->exec) {
+            cudaGraphExecDestroy(P->exec);
+            P->exec = nullptr;
+        }
+        cudaStream_t cap = P->stream;  // capture on the program's own stream, replay on the caller's
+        SBN_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+        const int64_t before = P->launches;
+        rc = issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, cap, nullptr);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        P->graph_launches = P->launches - before;
+        P->launches = before;
+        if (rc != SBN_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(SBN_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&P->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(SBN_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        k = {d_ev, ld_ev, n_rows, d_out, ld_out};
+    }
+    SBN_CUDA(cudaGraphLaunch(P->exec, stream));
+    P->launches += P->graph_launches;
+    return SBN_OK;
+}
+
+int sbn_program_run_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out, int64_t ld_out) {
+    int rc = check_run_args(P, ev, ld_ev, n_rows, out, ld_out);
+    if (rc != SBN_OK) return rc;
+    SBN_CUDA(cudaSetDevice(P->device));
+    if (P->reserved_rows == 0) {
+        rc = sbn_program_reserve(P, n_rows);
+        if (rc != SBN_OK) return rc;
+    }
+    const int64_t cap = P->reserved_rows;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += cap) {
+        const int64_t rows = std::min(cap, n_rows - r0);
+        if (P->n_ev > 0)
+            SBN_CUDA(cudaMemcpy2DAsync(P->d_ev, static_cast<size_t>(P->ld), ev + r0, static_cast<size_t>(ld_ev),
+                                       static_cast<size_t>(rows), static_cast<size_t>(P->n_ev), cudaMemcpyHostToDevice,
+                                       P->stream));
+        rc = sbn_program_run_device(P, P->d_ev, P->ld, rows, P->d_out, P->ld, P->stream);
+        if (rc != SBN_OK) return rc;
+        SBN_CUDA(cudaMemcpy2DAsync(out + r0, static_cast<size_t>(ld_out) * 4, P->d_out, static_cast<size_t>(P->ld) * 4,
+                                   static_cast<size_t>(rows) * 4, static_cast<size_t>(P->Q), cudaMemcpyDeviceToHost,
+                                   P->stream));
+    }
+    SBN_CUDA(cudaStreamSynchronize(P->stream));
+    return SBN_OK;
+}
+
+int sbn_program_profile(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                        int64_t ld_out, void *stream_, float *step_ms, int64_t n_step_ms) {
+    int rc = check_run_args(P, d_ev, ld_ev, n_rows, d_out, ld_out);
+    if (rc != SBN_OK) return rc;
+    const int64_t n = static_cast<int64_t>(P->steps.size()) + 1;
+    if (!step_ms || n_step_ms < n) return fail(SBN_E_INVALID, "step_ms needs %lld entries", (long long)n);
+    SBN_CUDA(cudaSetDevice(P->device));
+    if (P->reserved_rows == 0) {
+        rc = sbn_program_reserve(P, n_rows);
+        if (rc != SBN_OK) return rc;
+    }
+    if (n_rows > P->reserved_rows) return fail(SBN_E_INVALID, "n_rows exceeds the reserved chunk");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto &e : ev) SBN_CUDA(cudaEventCreate(&e));
+    rc = issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, stream, ev.data());
+    if (rc == SBN_OK) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) rc = fail(SBN_E_CUDA, "profile run failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == SBN_OK)
+        for (int64_t i = 0; i < n; ++i) cudaEventElapsedTime(&step_ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
+    if (!P || !info || n_info < 8) return fail(SBN_E_INVALID, "info needs 8 entries");
+    info[0] = P->Q;
+    info[1] = P->n_ev;
+    info[2] = static_cast<int64_t>(P->steps.size());
+    info[3] = batched_floats_per_row(P);
+    info[4] = P->reserved_rows;
+    info[5] = P->launches;
+    info[6] = P->mode;
+    int64_t shared = 0;
+    for (const Slot &s : P->slots)
+        if (!s.batched) shared += s.size;
+    info[7] = shared;
+    return SBN_OK;
+}
+
+int sbn_program_set_graph(sbn_program *P, int enabled) {
+    if (!P) return fail(SBN_E_INVALID, "null program");
+    P->use_graph = enabled != 0;
+    return SBN_OK;
+}
+
+int sbn_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(SBN_E_INVALID, "bad host allocation request");
+    SBN_CUDA(cudaHostAlloc(ptr, static_cast<size_t>(bytes), cudaHostAllocDefault));
+    return SBN_OK;
+}
+
+int sbn_host_free(void *ptr) {
+    if (ptr) SBN_CUDA(cudaFreeHost(ptr));
+    return SBN_OK;
+}
+
+}  // extern "C"

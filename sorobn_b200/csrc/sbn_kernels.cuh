@@ -1,0 +1,279 @@
+// sorobn_b200 -- sm_100a kernels for the factor-product / sum-out step.
+//
+// One launch computes, for every output entry o and evidence row b,
+//
+//     out[o, b] = sum_x prod_i in_i[ off_i(o) + x * sx_i + evoff_i(b) ]   (, b)
+//
+// which fuses `pointwise_mul` (/root/reference/sorobn/bayes_net.py:253-256: an
+// index join per pair of factors) with `sum_out` (bayes_net.py:54-103: a groupby-sum)
+// and with the evidence filter of bayes_net.py:772-774 (here a per-row gather).
+//
+// Data layout (DESIGN.md "HBM layout"):
+//   * batched factor  : float [scope..., ld]  -- evidence rows innermost, ld % 32 == 0,
+//                       so a warp reads 128 consecutive rows of one scope entry with
+//                       one 128-bit load per lane;
+//   * table / shared  : float [scope...]      -- a CPT or an evidence-independent
+//                       factor; small ones are staged in shared memory by a bulk-TMA
+//                       copy (cp.async.bulk -> SASS UBLKCP) and gathered per lane;
+//   * evidence codes  : uint8 [n_ev, ld_ev].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sorobn_b200.h"
+
+#define SBN_THREADS 128      // threads per CTA of the batched kernel (4 rows each)
+#define SBN_ROWS_PER_CTA (SBN_THREADS * 4)
+#define SBN_SMEM_BUDGET (64 * 1024)
+
+struct SbnInput {
+    const float *ptr;                // table / slot base (device)
+    int32_t batched;                 // 1: element offsets are in rows (x ld) plus b
+    int32_t sx;                      // stride of the eliminated axis
+    int32_t n_ev;                    // evidence axes gathered per row
+    int32_t smem_off;                // float offset of the staged copy, -1 = read global
+    int32_t stage_floats;            // floats copied by the bulk-TMA (multiple of 4)
+    int32_t pad_;
+    int32_t ev_col[SBN_MAX_EV];
+    int32_t ev_stride[SBN_MAX_EV];
+    int32_t ev_card[SBN_MAX_EV];     // codes are clamped to card-1 (no out-of-bounds gather)
+    int32_t stride[SBN_MAX_AXES];    // stride per output axis (0 = factor lacks the axis)
+};
+
+struct SbnStep {
+    float *out;
+    const uint8_t *ev;
+    int64_t ld_ev;
+    int64_t ld;          // row pitch of batched buffers (floats), multiple of 32
+    int32_t n_rows;      // valid evidence rows (<= ld)
+    int32_t n_in;
+    int32_t n_axes;
+    int32_t cx;          // states of the eliminated variable (1 = product only)
+    int32_t n_out;       // prod(card)
+    int32_t tile1;       // axis-1 digits handled by one CTA
+    int32_t n_tile1;     // ceil(card[1] / tile1)
+    int32_t n_bblocks;   // CTAs along the row axis
+    int32_t smem_floats; // staged floats in total
+    int32_t pad_;
+    int32_t card[SBN_MAX_AXES];
+    SbnInput in[SBN_MAX_IN];
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t sbn_smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void sbn_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sbn_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sbn_fence_mbar_init() {
+    // make the init visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sbn_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbn_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void sbn_tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    // 1-D bulk tensor-memory-accelerator copy global -> shared, completion on mbarrier
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sbn_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sbn_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sbn_mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(sbn_smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+__device__ __forceinline__ float4 sbn_mul4(float4 a, float4 b) {
+    return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+
+// ------------------------------------------------------------- batched step kernel
+// Grid: 1-D, blockIdx.x = tile * n_bblocks + bblock (row blocks fastest so that
+// neighbouring CTAs stream neighbouring rows of the same scope entries).
+// One CTA = 512 evidence rows x one tile of outputs: all card[0] digits of axis 0,
+// `tile1` digits of axis 1, one combination of the remaining axes.  The planner puts
+// the axes that the largest batched input lacks first, so the tile re-reads that
+// input's entries and they stay in L1.
+// Thread = 4 consecutive rows (one float4) looping over the tile; the eliminated axis
+// is reduced in-thread (strided float4 loads, each fully coalesced across the warp).
+template <int N_IN, int CX>
+__global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_constant__ SbnStep p) {
+    extern __shared__ __align__(16) float s_tab[];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const bool staged = p.smem_floats > 0;
+    if (staged) {
+        if (threadIdx.x == 0) {
+            sbn_mbar_init(&s_bar, 1);
+            sbn_fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sbn_mbar_expect_tx(&s_bar, static_cast<uint32_t>(p.smem_floats) * 4u);
+#pragma unroll
+            for (int i = 0; i < N_IN; ++i) {
+                if (p.in[i].smem_off >= 0) {
+                    sbn_tma_bulk_g2s(s_tab + p.in[i].smem_off, p.in[i].ptr,
+                                     static_cast<uint32_t>(p.in[i].stage_floats) * 4u, &s_bar);
+                }
+            }
+        }
+    }
+
+    const int bblock = blockIdx.x % p.n_bblocks;
+    int r = blockIdx.x / p.n_bblocks;  // tile id
+    const int b = (bblock * SBN_THREADS + threadIdx.x) * 4;
+    const bool live = b < p.n_rows;  // b % 4 == 0: the float4 holds at least one valid row
+
+    const int c0 = p.n_axes > 0 ? p.card[0] : 1;
+    const int c1 = p.n_axes > 1 ? p.card[1] : 1;
+    const int t1 = r % p.n_tile1;
+    r /= p.n_tile1;
+    const int d1_begin = t1 * p.tile1;
+    const int d1_end = min(c1, d1_begin + p.tile1);
+    const int o_rest = r * c0 * c1;  // output is contiguous in axis order
+
+    // mixed-radix digits of the remaining axes -> per-input base offsets (CTA-uniform)
+    int off[N_IN];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) off[i] = 0;
+    for (int j = 2; j < p.n_axes; ++j) {
+        const int c = p.card[j];
+        const int d = r % c;
+        r /= c;
+#pragma unroll
+        for (int i = 0; i < N_IN; ++i) off[i] += d * p.in[i].stride[j];
+    }
+
+    // per-row evidence offsets of the gathered tables
+    int evo[N_IN][4];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) {
+        evo[i][0] = evo[i][1] = evo[i][2] = evo[i][3] = 0;
+        if (!p.in[i].batched && live) {
+            for (int k = 0; k < p.in[i].n_ev; ++k) {
+                const uint8_t *col = p.ev + static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev + b;
+                const int s = p.in[i].ev_stride[k];
+                const int top = p.in[i].ev_card[k] - 1;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const int code = (b + l < p.n_rows) ? min(static_cast<int>(col[l]), top) : 0;
+                    evo[i][l] += code * s;
+                }
+            }
+        }
+    }
+
+    if (staged) sbn_mbar_wait(&s_bar, 0);
+    if (!live) return;
+
+    const int cx = CX > 0 ? CX : p.cx;
+    const int64_t ld = p.ld;
+
+    for (int d1 = d1_begin; d1 < d1_end; ++d1) {
+        int e0[N_IN];
+#pragma unroll
+        for (int i = 0; i < N_IN; ++i) e0[i] = off[i] + d1 * (p.n_axes > 1 ? p.in[i].stride[1] : 0);
+        for (int d0 = 0; d0 < c0; ++d0) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto term = [&](int x) {
+                float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int i = 0; i < N_IN; ++i) {
+                    const int e = e0[i] + x * p.in[i].sx;
+                    float4 v;
+                    if (p.in[i].batched) {
+                        v = *reinterpret_cast<const float4 *>(p.in[i].ptr + static_cast<int64_t>(e) * ld + b);
+                    } else if (p.in[i].smem_off >= 0) {
+                        const float *t = s_tab + p.in[i].smem_off + e;
+                        v = make_float4(t[evo[i][0]], t[evo[i][1]], t[evo[i][2]], t[evo[i][3]]);
+                    } else {
+                        const float *t = p.in[i].ptr + e;
+                        v = make_float4(__ldg(t + evo[i][0]), __ldg(t + evo[i][1]), __ldg(t + evo[i][2]),
+                                        __ldg(t + evo[i][3]));
+                    }
+                    prod = sbn_mul4(prod, v);
+                }
+                acc.x += prod.x;
+                acc.y += prod.y;
+                acc.z += prod.z;
+                acc.w += prod.w;
+            };
+            if constexpr (CX > 0) {
+#pragma unroll
+                for (int x = 0; x < CX; ++x) term(x);
+            } else {
+#pragma unroll 4
+                for (int x = 0; x < cx; ++x) term(x);
+            }
+            *reinterpret_cast<float4 *>(p.out + static_cast<int64_t>(o_rest + d1 * c0 + d0) * ld + b) = acc;
+#pragma unroll
+            for (int i = 0; i < N_IN; ++i) e0[i] += p.n_axes > 0 ? p.in[i].stride[0] : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- flat step kernel
+// Evidence-independent factors (and single-row "flat" programs): one thread per
+// output entry, mixed-radix decomposition of the entry index in registers, the
+// eliminated axis reduced in-thread.  Evidence offsets are uniform (row 0).
+__global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ SbnStep p) {
+    const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (o >= p.n_out) return;
+    int off[SBN_MAX_IN];
+#pragma unroll
+    for (int i = 0; i < SBN_MAX_IN; ++i) {
+        off[i] = 0;
+        if (i < p.n_in) {
+            for (int k = 0; k < p.in[i].n_ev; ++k)
+                off[i] += min(static_cast<int>(p.ev[static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev]),
+                              p.in[i].ev_card[k] - 1) *
+                          p.in[i].ev_stride[k];
+        }
+    }
+    int r = static_cast<int>(o);
+    for (int j = 0; j < p.n_axes; ++j) {
+        const int c = p.card[j];
+        const int d = r % c;
+        r /= c;
+#pragma unroll
+        for (int i = 0; i < SBN_MAX_IN; ++i)
+            if (i < p.n_in) off[i] += d * p.in[i].stride[j];
+    }
+    float acc = 0.f;
+    for (int x = 0; x < p.cx; ++x) {
+        float prod = 1.f;
+#pragma unroll
+        for (int i = 0; i < SBN_MAX_IN; ++i)
+            if (i < p.n_in) prod *= __ldg(p.in[i].ptr + off[i] + x * p.in[i].sx);
+        acc += prod;
+    }
+    p.out[o] = acc;
+}
+
+// ---------------------------------------------------------------------- normalise
+// posterior[q, b] = post[q, b] / sum_q post[q, b]   (bayes_net.py:789-790)
+// One thread per evidence row; reads are coalesced across rows for every q.
+__global__ void __launch_bounds__(256)
+sbn_normalise(const float *__restrict__ post, int64_t ld, int post_batched, int Q, float *__restrict__ out,
+              int64_t ld_out, int n_rows) {
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= n_rows) return;
+    const int64_t pitch = post_batched ? ld : 0;
+    const int64_t base = post_batched ? b : 0;
+    float total = 0.f;
+    for (int q = 0; q < Q; ++q) total += post[q * (post_batched ? pitch : 1) + base];
+    for (int q = 0; q < Q; ++q) out[q * ld_out + b] = post[q * (post_batched ? pitch : 1) + base] / total;
+}

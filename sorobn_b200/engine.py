@@ -1,0 +1,192 @@
+"""ctypes shim over libsorobn_b200.so (the C ABI in include/sorobn_b200.h).
+
+This is the "thin C-ABI/ctypes shim" between the Python host (`BayesNet.query`) and
+the CUDA kernels.  There is deliberately no fallback: if the library has not been
+built (`python -m sorobn_b200.csrc.build` / `__graft_entry__.build()`), cannot be
+loaded, or no sm_100 GPU is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_b200.so")
+_lib = None
+
+SBN_OK = 0
+ABI_VERSION = 2
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library and declare every entry point of include/sorobn_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise EngineError(
+            f"{_LIB_PATH} is missing: build the CUDA library first "
+            "(python -m sorobn_b200.csrc.build, or __graft_entry__.build()). "
+            "sorobn_b200 has no CPU fallback for exact inference."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    c = ctypes
+    vp, i64, i32 = c.c_void_p, c.c_int64, c.c_int
+    lib.sbn_abi_version.restype = i32
+    lib.sbn_abi_version.argtypes = []
+    lib.sbn_last_error.restype = c.c_char_p
+    lib.sbn_last_error.argtypes = []
+    lib.sbn_device_count.restype = i32
+    lib.sbn_device_count.argtypes = [c.POINTER(i32)]
+    lib.sbn_program_create.restype = i32
+    lib.sbn_program_create.argtypes = [i32, vp, i64, vp, i64, c.POINTER(vp)]
+    lib.sbn_program_destroy.restype = None
+    lib.sbn_program_destroy.argtypes = [vp]
+    lib.sbn_program_reserve.restype = i32
+    lib.sbn_program_reserve.argtypes = [vp, i64]
+    lib.sbn_program_run_host.restype = i32
+    lib.sbn_program_run_host.argtypes = [vp, vp, i64, i64, vp, i64]
+    lib.sbn_program_run_device.restype = i32
+    lib.sbn_program_run_device.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+    lib.sbn_program_profile.restype = i32
+    lib.sbn_program_profile.argtypes = [vp, vp, i64, i64, vp, i64, vp, vp, i64]
+    lib.sbn_program_info.restype = i32
+    lib.sbn_program_info.argtypes = [vp, vp, i64]
+    lib.sbn_program_set_graph.restype = i32
+    lib.sbn_program_set_graph.argtypes = [vp, i32]
+    lib.sbn_host_alloc.restype = i32
+    lib.sbn_host_alloc.argtypes = [c.POINTER(vp), i64]
+    lib.sbn_host_free.restype = i32
+    lib.sbn_host_free.argtypes = [vp]
+    if lib.sbn_abi_version() != ABI_VERSION:
+        raise EngineError(f"libsorobn_b200.so has ABI {lib.sbn_abi_version()}, Python expects {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+EXPORTS = (
+    "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_destroy",
+    "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
+    "sbn_program_info", "sbn_program_set_graph", "sbn_host_alloc", "sbn_host_free",
+)
+
+
+def _check(rc: int):
+    if rc != SBN_OK:
+        raise EngineError(f"libsorobn_b200 error {rc}: {load().sbn_last_error().decode(errors='replace')}")
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    rc = load().sbn_device_count(ctypes.byref(n))
+    return n.value if rc == SBN_OK else 0
+
+
+def default_device() -> int:
+    return int(os.environ.get("SOROBN_B200_DEVICE", "0"))
+
+
+class PinnedArray:
+    """A numpy array backed by page-locked host memory (cudaHostAlloc) so that the
+    engine's host<->device copies are true asynchronous DMA."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        self._ptr = ctypes.c_void_p()
+        _check(load().sbn_host_alloc(ctypes.byref(self._ptr), nbytes))
+        buf = (ctypes.c_char * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            load().sbn_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Program:
+    """One compiled (query variables, evidence variables) pair on one GPU."""
+
+    def __init__(self, plan, device: int | None = None):
+        lib = load()
+        self.plan = plan
+        self.device = default_device() if device is None else int(device)
+        self.Q = int(plan.Q)
+        self.n_ev = len(plan.evidence)
+        self._h = ctypes.c_void_p()
+        words = np.ascontiguousarray(plan.words, dtype=np.int32)
+        blob = np.ascontiguousarray(plan.table_blob, dtype=np.float32)
+        _check(lib.sbn_program_create(self.device, words.ctypes.data, words.size, blob.ctypes.data, blob.size,
+                                      ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load().sbn_program_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ control
+    def reserve(self, max_rows: int):
+        _check(load().sbn_program_reserve(self._h, int(max_rows)))
+
+    def set_graph(self, enabled: bool):
+        _check(load().sbn_program_set_graph(self._h, int(bool(enabled))))
+
+    def info(self) -> dict:
+        buf = (ctypes.c_int64 * 8)()
+        _check(load().sbn_program_info(self._h, buf, 8))
+        keys = ("Q", "n_ev", "n_steps", "scratch_floats_per_row", "reserved_rows", "launches", "mode",
+                "shared_scratch_floats")
+        return dict(zip(keys, [int(x) for x in buf]))
+
+    # --------------------------------------------------------------------- runs
+    def run(self, codes: np.ndarray, n_rows: int, out: np.ndarray | None = None) -> np.ndarray:
+        """Host path: evidence codes uint8 [n_ev, n_rows] in, posterior float32
+        [Q, n_rows] out (copies H2D, every step, D2H, synchronises)."""
+        n_rows = int(n_rows)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if self.n_ev:
+            if codes.shape != (self.n_ev, n_rows):
+                raise ValueError(f"evidence codes have shape {codes.shape}, expected {(self.n_ev, n_rows)}")
+        if out is None:
+            out = np.empty((self.Q, n_rows), dtype=np.float32)
+        elif out.shape != (self.Q, n_rows) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 [Q, n_rows] array")
+        ev_ptr = codes.ctypes.data if self.n_ev else None
+        _check(load().sbn_program_run_host(self._h, ev_ptr, n_rows, n_rows, out.ctypes.data, n_rows))
+        return out
+
+    def run_device(self, d_ev: int, ld_ev: int, n_rows: int, d_out: int, ld_out: int, stream: int = 0):
+        """Device path: raw device pointers, asynchronous on `stream`."""
+        _check(load().sbn_program_run_device(self._h, ctypes.c_void_p(d_ev), int(ld_ev), int(n_rows),
+                                             ctypes.c_void_p(d_out), int(ld_out), ctypes.c_void_p(stream)))
+
+    def profile(self, d_ev: int, ld_ev: int, n_rows: int, d_out: int, ld_out: int, stream: int = 0) -> np.ndarray:
+        n = len(self.plan.steps) + 1
+        ms = np.zeros(n, dtype=np.float32)
+        _check(load().sbn_program_profile(self._h, ctypes.c_void_p(d_ev), int(ld_ev), int(n_rows),
+                                          ctypes.c_void_p(d_out), int(ld_out), ctypes.c_void_p(stream),
+                                          ms.ctypes.data, n))
+        return ms

@@ -1,0 +1,403 @@
+"""Variable-elimination planner: (network, query vars, evidence vars) -> device program.
+
+The reference interleaves planning and arithmetic inside
+`BayesNet._variable_elimination` (/root/reference/sorobn/bayes_net.py:739-794):
+it works out the relevant and hidden nodes, slices every CPT by the event, then for
+each hidden node multiplies the factors that mention it (`pointwise_mul`,
+bayes_net.py:253) and sums it out (`CDTAccessor.sum_out`, bayes_net.py:54).
+
+Here the same decisions are taken once per (query vars, evidence vars) pair and
+frozen into a flat int32 program; the arithmetic then runs on the device for any
+number of evidence rows.  Each program step is one fused
+"product of k factors -> sum out one axis" kernel launch:
+
+    out[o, b] = sum_x  prod_i  in_i[ off_i(o) + x * sx_i + evoff_i(b) ]   (, b)
+
+* `o` runs over the output scope (mixed radix, axis 0 fastest), `b` over evidence
+  rows.  A factor that depends on the evidence is *batched*: stored `[scope..., B]`
+  with the row axis innermost so that a warp reads 32 x 4 consecutive rows of one
+  scope entry with 128-bit loads.
+* Evidence never materialises sliced tables: a CPT axis that belongs to an
+  evidence variable is indexed per row with that row's state code
+  (`evoff_i(b) = sum_k ev[col_k, b] * stride_k`).
+* Factors that do not depend on evidence stay unbatched and are computed once per
+  call by the flat kernel.
+
+Program layout (int32 words) -- parsed by csrc/sbn_api.cu and by
+oracle/program_interp.py (the CPU checker used in tests):
+
+    header : MAGIC VERSION mode n_ev n_tables n_slots n_steps Q post_slot post_batched 0 0
+    tables : (offset_floats, size) * n_tables         -- into the float table blob
+    slots  : (batched, size_per_row) * n_slots        -- scratch buffers
+    steps  : kind n_in out_slot n_axes cX | cards[n_axes] |
+             per input: is_slot id batched sx n_ev (col stride card)*n_ev strides[n_axes]
+
+`mode` 0 = flat (one evidence row, nothing batched: evidence offsets are uniform),
+1 = batched.  The posterior is produced by the last step into `post_slot`
+(`[Q]` or `[Q, B]`, unnormalised) and normalised per row by the engine.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MAGIC = 0x53424E31  # "SBN1"
+VERSION = 3
+MAX_IN = 8  # factors fused per launch (csrc/sbn_kernels.cuh: SBN_MAX_IN)
+MAX_AXES = 20  # output axes per step (SBN_MAX_AXES)
+MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
+MODE_FLAT, MODE_BATCHED = 0, 1
+KIND_FLAT, KIND_BATCHED = 0, 1
+HEADER_WORDS = 12
+
+
+@dataclass
+class CompiledNet:
+    """Dense, integer-indexed form of a prepared BayesNet (built by
+    `BayesNet.prepare()`; the analogue of the pandas housekeeping at
+    bayes_net.py:327-371 plus "ship the tables to the device")."""
+
+    names: list  # var id -> node name, topological order (== BayesNet.nodes)
+    domains: list  # var id -> sorted list of state values
+    parents: list  # var id -> list of parent ids (sorted by name, like the reference)
+    cpt: list  # var id -> float64 ndarray, axes [*parents, var]
+    card: np.ndarray = None
+    index: dict = field(default_factory=dict)  # name -> var id
+
+    def __post_init__(self):
+        self.card = np.array([len(d) for d in self.domains], dtype=np.int64)
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+    def scope(self, v):
+        return (*self.parents[v], v)
+
+    def ancestors(self, v):
+        seen = set()
+        stack = list(self.parents[v])
+        while stack:
+            p = stack.pop()
+            if p not in seen:
+                seen.add(p)
+                stack.extend(self.parents[p])
+        return seen
+
+
+@dataclass
+class _Factor:
+    is_slot: bool
+    buf: int  # table index or slot index
+    vars: tuple  # free variable ids
+    strides: tuple  # element stride per free variable
+    ev: tuple  # ((ev_col, stride, card), ...) -- only raw tables carry these
+    batched: bool
+
+    @property
+    def depends_on_evidence(self):
+        return self.batched or bool(self.ev)
+
+
+@dataclass
+class Step:
+    kind: int
+    inputs: list  # of (factor, sx, strides-per-out-axis)
+    out_slot: int
+    out_vars: tuple  # axis 0 (fastest) first
+    cards: tuple
+    cx: int
+    elim: int | None
+
+
+@dataclass
+class Plan:
+    mode: int
+    query: tuple  # query var ids, in output (sorted-name) order, slowest axis first
+    evidence: tuple  # evidence var ids == evidence columns
+    order: list  # elimination order (var ids)
+    tables: list  # var ids whose CPTs are shipped, in table order
+    table_scale_log2: list
+    slots: list  # (batched, size)
+    steps: list
+    post_slot: int
+    Q: int
+    words: np.ndarray = None
+    table_blob: np.ndarray = None
+    table_blob64: np.ndarray = None
+    table_offsets: list = None
+
+    # ---- cost model (DESIGN.md "algorithmic bytes") -------------------------------
+    def bytes_per_row(self):
+        """Algorithmic HBM bytes per evidence row: every batched step reads each
+        batched input once and writes its output once (fp32), plus the evidence
+        codes in and the posterior out."""
+        total = 0
+        for st in self.steps:
+            if st.kind != KIND_BATCHED:
+                continue
+            for f, _, _ in st.inputs:
+                if f.batched:
+                    total += 4 * int(np.prod([self._card[v] for v in f.vars], dtype=np.int64))
+            total += 4 * int(np.prod(st.cards, dtype=np.int64))
+        # normalise: read unnormalised posterior, write posterior
+        total += 8 * self.Q
+        total += len(self.evidence)  # uint8 codes
+        return total
+
+    def step_bytes_per_row(self):
+        out = []
+        for st in self.steps:
+            if st.kind != KIND_BATCHED:
+                out.append(0)
+                continue
+            t = 4 * int(np.prod(st.cards, dtype=np.int64))
+            for f, _, _ in st.inputs:
+                if f.batched:
+                    t += 4 * int(np.prod([self._card[v] for v in f.vars], dtype=np.int64))
+            out.append(t)
+        return out
+
+    def flops_per_row(self):
+        total = 0
+        for st in self.steps:
+            if st.kind != KIND_BATCHED:
+                continue
+            total += int(np.prod(st.cards, dtype=np.int64)) * st.cx * len(st.inputs)
+        return total
+
+    def scratch_floats_per_row(self):
+        return sum(size for batched, size in self.slots if batched)
+
+    def max_factor_per_row(self):
+        return max([size for batched, size in self.slots if batched] or [0])
+
+
+def _min_fill_order(scopes, hidden, card):
+    """Greedy min-fill (ties: smaller clique, then lower var id).  The reference
+    eliminates in set-iteration order (bayes_net.py:779), which is arbitrary and
+    does not change the answer; BASELINE.json asks for min-fill."""
+    adj = {}
+    for sc in scopes:
+        for a in sc:
+            adj.setdefault(a, set()).update(b for b in sc if b != a)
+    for h in hidden:
+        adj.setdefault(h, set())
+    remaining = sorted(hidden)
+    order = []
+    while remaining:
+        best_key, best_v = None, None
+        for v in remaining:
+            nb = list(adj[v])
+            fill = 0
+            for i in range(len(nb)):
+                ai = adj[nb[i]]
+                for j in range(i + 1, len(nb)):
+                    if nb[j] not in ai:
+                        fill += 1
+            size = 1
+            for u in nb:
+                size *= int(card[u])
+            key = (fill, size, v)
+            if best_key is None or key < best_key:
+                best_key, best_v = key, v
+        v = best_v
+        nb = adj.pop(v)
+        for a in nb:
+            adj[a].discard(v)
+            adj[a].update(b for b in nb if b != a)
+        remaining.remove(v)
+        order.append(v)
+    return order
+
+
+def table_scale_log2(table: np.ndarray) -> int:
+    """Power-of-two exponent k such that table * 2**k has geometric mean ~1 over
+    its positive entries.  Scaling a CPT by a constant cancels in the final
+    normalisation (bayes_net.py:790) and a power of two is exact in fp32; it keeps
+    products of ~100 probabilities away from fp32 underflow."""
+    pos = table[table > 0]
+    if pos.size == 0:
+        return 0
+    k = -int(np.round(np.mean(np.log2(pos))))
+    return int(np.clip(k, -60, 60))
+
+
+def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN) -> Plan:
+    """Plan P(query | evidence) for `net`.
+
+    query / evidence are sequences of var ids.  `evidence` fixes the evidence
+    *columns*; their values arrive at run time.
+    """
+    query = tuple(query)
+    evidence = tuple(evidence)
+    if not query:
+        # bayes_net.py:840-841
+        raise ValueError("At least one query variable has to be specified")
+    if set(query) & set(evidence):
+        # bayes_net.py:843-845
+        raise ValueError("A query variable cannot be part of the event")
+    if len(set(query)) != len(query) or len(set(evidence)) != len(evidence):
+        raise ValueError("duplicate variable in query or event")
+    card = net.card
+    for v in evidence:
+        if card[v] > 255:
+            raise ValueError(f"evidence variable {net.names[v]!r} has {card[v]} states; state codes are uint8")
+
+    # bayes_net.py:763-766
+    relevant = {*query, *evidence}
+    for v in list(relevant):
+        relevant |= net.ancestors(v)
+    hidden = relevant - set(query) - set(evidence)
+    ev_col = {v: i for i, v in enumerate(evidence)}
+
+    # bayes_net.py:768-776 -- one factor per relevant CPT; evidence axes become
+    # per-row gathers instead of boolean filters
+    tables = sorted(relevant)
+    factors = []
+    for t, v in enumerate(tables):
+        scope = net.scope(v)
+        shape = [int(card[u]) for u in scope]
+        strides = [int(np.prod(shape[i + 1:], dtype=np.int64)) for i in range(len(shape))]
+        free = [(u, s) for u, s in zip(scope, strides) if u not in ev_col]
+        ev = tuple((ev_col[u], s, int(card[u])) for u, s in zip(scope, strides) if u in ev_col)
+        if len(ev) > MAX_EV:
+            raise ValueError(f"CPT of {net.names[v]!r} has {len(ev)} evidence axes; the kernel supports {MAX_EV}")
+        factors.append(_Factor(False, t, tuple(u for u, _ in free), tuple(s for _, s in free), ev, False))
+
+    if order is None:
+        order = _min_fill_order([f.vars for f in factors], hidden, card)
+    else:
+        order = list(order)
+        if set(order) != hidden or len(order) != len(hidden):
+            raise ValueError("elimination order must be a permutation of the hidden variables")
+
+    slots = []  # physical: [batched, size, free?]
+    steps = []
+
+    def alloc(batched, size):
+        best = None
+        for i, (b, s, free) in enumerate(slots):
+            if free and b == batched and s >= size and (best is None or s < slots[best][1]):
+                best = i
+        if best is None:
+            slots.append([batched, size, False])
+            return len(slots) - 1
+        slots[best][2] = False
+        return best
+
+    def release(f):
+        if f.is_slot:
+            slots[f.buf][2] = True
+
+    def emit(inputs, elim, out_vars):
+        """One fused launch: multiply `inputs`, sum out `elim` (None: product only).
+        out_vars is given fastest axis first."""
+        dep = any(f.depends_on_evidence for f in inputs)
+        batched = dep and mode == MODE_BATCHED
+        if len(out_vars) > MAX_AXES:
+            raise ValueError(f"a factor over {len(out_vars)} variables exceeds the kernel's {MAX_AXES} axes")
+        cards = tuple(int(card[u]) for u in out_vars)
+        size = int(np.prod(cards, dtype=np.int64)) if cards else 1
+        if size >= 2**31:
+            raise ValueError("a factor with >= 2^31 entries per row does not fit the 32-bit scope index")
+        out_slot = alloc(batched, size)
+        ins = []
+        for f in inputs:
+            pos = {u: s for u, s in zip(f.vars, f.strides)}
+            ins.append((f, pos.get(elim, 0) if elim is not None else 0, tuple(pos.get(u, 0) for u in out_vars)))
+        steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_slot, tuple(out_vars), cards,
+                          int(card[elim]) if elim is not None else 1, elim))
+        for f in inputs:
+            release(f)
+        out_strides = []
+        acc = 1
+        for c in cards:
+            out_strides.append(acc)
+            acc *= c
+        return _Factor(True, out_slot, tuple(out_vars), tuple(out_strides), (), batched)
+
+    def fsize(f):
+        return int(np.prod([card[u] for u in f.vars], dtype=np.int64)) if f.vars else 1
+
+    def axis_order(inputs, out_set):
+        """Fastest-first order of the output axes.  Axes that the largest batched
+        input does not have go first (its entries are then re-used by consecutive
+        outputs, which the kernel's o-tile keeps in registers/L1); the rest follow
+        that input's own order so its reads stay sequential."""
+        big = max(inputs, key=lambda f: (f.batched, fsize(f)))
+        in_big = [u for _, u in sorted(zip(big.strides, big.vars)) if u in out_set]
+        new = sorted(u for u in out_set if u not in big.vars)
+        return new + in_big
+
+    def product_chain(inputs, elim, final_vars=None):
+        inputs = list(inputs)
+        # bayes_net.py:256 reduces pairwise; fuse up to max_in factors per launch and
+        # fold the smallest ones first when there are more
+        while len(inputs) > max_in:
+            inputs.sort(key=fsize)
+            head, inputs = inputs[:max_in], inputs[max_in:]
+            union = set().union(*[f.vars for f in head])
+            inputs.append(emit(head, None, axis_order(head, union)))
+        union = set().union(*[f.vars for f in inputs]) if inputs else set()
+        if final_vars is not None:
+            assert union == set(final_vars), (union, final_vars)
+            return emit(inputs, None, list(final_vars))
+        out_set = union - {elim}
+        return emit(inputs, elim, axis_order(inputs, out_set))
+
+    # bayes_net.py:778-786
+    for x in order:
+        touching = [f for f in factors if x in f.vars]
+        factors = [f for f in factors if x not in f.vars]
+        factors.append(product_chain(touching, x))
+
+    # bayes_net.py:788-794: product of what is left; the answer's levels are sorted
+    # by name (bayes_net.py:872-873) and rows by state (sort_index, :875)
+    q_sorted = tuple(sorted(query, key=lambda v: net.names[v]))
+    post = product_chain(factors, None, final_vars=tuple(reversed(q_sorted)))
+    Q = fsize(post)
+
+    plan = Plan(mode=mode, query=q_sorted, evidence=evidence, order=list(order), tables=tables,
+                table_scale_log2=[table_scale_log2(net.cpt[v]) for v in tables],
+                slots=[(bool(b), int(s)) for b, s, _ in slots], steps=steps, post_slot=post.buf, Q=Q)
+    plan._card = card
+    _serialise(plan, net)
+    return plan
+
+
+def _serialise(plan: Plan, net: CompiledNet):
+    blob = []
+    offsets = []
+    off = 0
+    for v, k in zip(plan.tables, plan.table_scale_log2):
+        t = np.ldexp(net.cpt[v].astype(np.float64), k).reshape(-1)
+        pad = (-t.size) % 4  # keep every table 16-byte aligned and sized (bulk-TMA copies)
+        offsets.append((off, t.size))
+        blob.append(t)
+        if pad:
+            blob.append(np.zeros(pad, dtype=np.float64))
+        off += t.size + pad
+    # float64 copy: only the CPU checker (oracle/program_interp.py) reads it, to
+    # separate planner errors from fp32 rounding; the device gets the fp32 blob
+    plan.table_blob64 = np.concatenate(blob) if blob else np.zeros(0, dtype=np.float64)
+    plan.table_blob = plan.table_blob64.astype(np.float32)
+    plan.table_offsets = offsets
+
+    w = [MAGIC, VERSION, plan.mode, len(plan.evidence), len(plan.tables), len(plan.slots), len(plan.steps),
+         plan.Q, plan.post_slot, int(plan.slots[plan.post_slot][0]), 0, 0]
+    assert len(w) == HEADER_WORDS
+    for o, s in offsets:
+        w += [o, s]
+    for b, s in plan.slots:
+        w += [int(b), s]
+    for st in plan.steps:
+        w += [st.kind, len(st.inputs), st.out_slot, len(st.cards), st.cx]
+        w += list(st.cards)
+        for f, sx, strides in st.inputs:
+            w += [int(f.is_slot), f.buf, int(f.batched), sx, len(f.ev)]
+            for col, s, c in f.ev:
+                w += [col, s, c]
+            w += list(strides)
+    arr = np.asarray(w, dtype=np.int64)
+    if arr.max(initial=0) >= 2**31:
+        raise ValueError("program word overflows int32")
+    plan.words = arr.astype(np.int32)

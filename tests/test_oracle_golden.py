@@ -1,0 +1,103 @@
+"""Pin the CPU oracle (oracle/ve_oracle.py) against the reference.
+
+The golden vectors were produced by the real reference (oracle/gen_golden.py); the
+hand-written values below are the reference's own doctest outputs
+(/root/reference/sorobn/bayes_net.py and examples.py)."""
+import numpy as np
+import pytest
+
+from conftest import build_network, case_event, dense_answer, golden_names, load_golden
+from oracle import ve_oracle
+
+
+def oracle_net(bn):
+    return ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference_goldens(name):
+    golden = load_golden(name)
+    bn = build_network(golden)
+    net = oracle_net(bn)
+    worst = 0.0
+    for case in golden["cases"]:
+        vars_, values, support = ve_oracle.query(net, *case["query"], event=case_event(case))
+        assert list(vars_) == case["names"]
+        want = dense_answer(case, net.domains)
+        # same support: the reference drops exactly the zero-posterior rows
+        assert np.array_equal(support, want > 0), case
+        err = np.max(np.abs(values - want) / np.maximum(want, 1e-300) * (want > 0))
+        worst = max(worst, err)
+    assert worst < 1e-12, worst
+
+
+def test_aima_figure_14_10_product_and_sum_out():
+    # doctest of pointwise_mul_two / sum_out, bayes_net.py:62-97 and :114-140
+    a = ve_oracle.Factor(("A", "B"), np.array([[0.1, 0.9], [0.7, 0.3]]))  # states sorted F, T
+    b = ve_oracle.Factor(("B", "C"), np.array([[0.4, 0.6], [0.8, 0.2]]))
+    ab = ve_oracle.pointwise_mul_two(a, b)
+    assert ab.vars == ("A", "B", "C")
+    # (A=T, B=T, C=T) = .3 * .2
+    assert np.isclose(ab.values[1, 1, 1], 0.06)
+    assert np.isclose(ab.values[1, 0, 0], 0.28)
+    assert np.isclose(ab.values[0, 1, 0], 0.72)
+    s = ve_oracle.sum_out(ab, "B")
+    assert s.vars == ("A", "C")
+    assert np.allclose(s.values, [[0.76, 0.24], [0.52, 0.48]])
+
+
+def test_disjoint_product_is_outer():
+    # bayes_net.py:145-179
+    a = ve_oracle.Factor(("A",), np.array([0.7, 0.3]))
+    b = ve_oracle.Factor(("B",), np.array([0.8, 0.2]))
+    ab = ve_oracle.pointwise_mul_two(a, b)
+    assert np.allclose(ab.values, np.outer([0.7, 0.3], [0.8, 0.2]))
+
+
+def test_reference_doctest_values():
+    from sorobn_b200 import examples
+
+    # bayes_net.py:751-755
+    net = oracle_net(examples.sprinkler())
+    _, v, _ = ve_oracle.query(net, "Rain", event={"Sprinkler": True})
+    assert np.allclose(v, [0.7, 0.3])
+    # bayes_net.py:829-836
+    net = oracle_net(examples.asia())
+    vars_, v, _ = ve_oracle.query(net, "Lung cancer", "Tuberculosis", event={"Visit to Asia": True, "Smoker": True})
+    assert vars_ == ("Lung cancer", "Tuberculosis")
+    assert np.allclose(v, [[0.855, 0.045], [0.095, 0.005]])
+    # examples.py:21-27
+    net = oracle_net(examples.alarm())
+    _, v, _ = ve_oracle.query(net, "John calls", "Mary calls", event={"Burglary": True, "Earthquake": False})
+    assert np.allclose(v, [[0.08463, 0.06637], [0.25677, 0.59223]])
+    # examples.py:268-274
+    net = oracle_net(examples.grades())
+    _, v, _ = ve_oracle.query(net, "Letter", "SAT", event={"Intelligence": "Smart"})
+    assert np.allclose(v, [[0.153544, 0.614176], [0.046456, 0.185824]], atol=1e-6)
+
+
+def test_elimination_order_does_not_matter():
+    from sorobn_b200 import examples
+
+    net = oracle_net(examples.asia())
+    hidden_orders = [
+        ["Tuberculosis", "Lung cancer", "Bronchitis", "TB or cancer", "Smoker"],
+        ["Smoker", "TB or cancer", "Bronchitis", "Lung cancer", "Tuberculosis"],
+    ]
+    ev = {"Visit to Asia": True, "Positive X-ray": True}
+    base = ve_oracle.query(net, "Dispnea", event=ev)[1]
+    for order in hidden_orders:
+        assert np.allclose(ve_oracle.query(net, "Dispnea", event=ev, order=order)[1], base, rtol=1e-13)
+    # and equals brute force over the full joint (bayes_net.py:398-465)
+    _, bf = ve_oracle.brute_force_query(net, ("Dispnea",), ev)
+    assert np.allclose(bf, base, rtol=1e-12)
+
+
+def test_query_argument_errors():
+    from sorobn_b200 import examples
+
+    net = oracle_net(examples.alarm())
+    with pytest.raises(ValueError):
+        ve_oracle.query(net, event={})
+    with pytest.raises(ValueError):
+        ve_oracle.query(net, "Alarm", event={"Alarm": True})
