@@ -96,6 +96,10 @@ int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 /* Toggle CUDA-graph replay of the step sequence (default on). */
 int sbn_program_set_graph(sbn_program *prog, int enabled);
 
+/* Toggle the register-tiled step kernel (default on; off = the plain one-output-per-
+ * iteration kernel, kept as the general fallback and as a cross-check in tests). */
+int sbn_program_set_tiled(sbn_program *prog, int enabled);
+
 /* Pinned host memory for evidence / posterior staging buffers. */
 int sbn_host_alloc(void **ptr, int64_t bytes);
 int sbn_host_free(void *ptr);

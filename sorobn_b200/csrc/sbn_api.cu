@@ -60,6 +60,10 @@ struct StepDesc {
     int64_t n_out;
     std::vector<int> cards;
     std::vector<InDesc> in;
+    // tiled fast path (sbn_step_tiled): tile edge, tile count, offset-table position
+    int tile = 0;            // 0 = not eligible, use sbn_step_batched
+    int64_t n_tiles = 0;
+    int64_t tile_off_pos = 0;  // int32 offset into sbn_program::d_tile_off
 };
 struct Slot {
     bool batched;
@@ -85,11 +89,13 @@ struct sbn_program {
     int64_t ld = 0;             // row pitch of batched scratch (floats)
     float *d_arena = nullptr;   // batched scratch
     float *d_shared = nullptr;  // unbatched scratch
+    int32_t *d_tile_off = nullptr;  // per-step tile offset tables of the tiled kernel
     uint8_t *d_ev = nullptr;    // staging for run_host  [n_ev][ld]
     float *d_out = nullptr;     //                         [Q][ld]
     cudaStream_t stream = nullptr;
 
     bool use_graph = true;
+    bool use_tiled = true;
     cudaGraphExec_t exec = nullptr;
     struct {
         const uint8_t *ev;
@@ -100,7 +106,6 @@ struct sbn_program {
     int64_t graph_launches = 0;
 
     int64_t launches = 0;
-    int max_dyn_smem_set = 0;
 };
 
 namespace {
@@ -221,6 +226,71 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
     return SBN_OK;
 }
 
+constexpr int kTiledV = 2;             // evidence rows per thread of the tiled kernel
+constexpr int kTiledMaxIn = 4;
+constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
+
+// Host half of the tiled kernel: pick the tile edge and precompute, for every tile, the
+// output entry and each input's element offset (the row-invariant mixed-radix
+// decomposition, hoisted out of the kernel).
+void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
+    for (StepDesc &st : P->steps) {
+        st.tile = 0;
+        if (st.kind != 1 || st.in.size() > static_cast<size_t>(kTiledMaxIn)) continue;
+        int64_t smem = 0;
+        for (const InDesc &in : st.in)
+            if (!in.batched) smem += in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
+        if (smem * 4 > SBN_SMEM_BUDGET) continue;
+        const int n_axes = static_cast<int>(st.cards.size());
+        const int c0 = n_axes > 0 ? st.cards[0] : 1;
+        const int c1 = n_axes > 1 ? st.cards[1] : 1;
+        if (c0 > 255 * 5 || c1 > 255 * 5) continue;
+        // tile edge: least padding waste, ties to the larger tile
+        int best_t = 2;
+        double best_w = 1e30;
+        for (int t = 2; t <= 5; ++t) {
+            auto waste = [&](int c) { return static_cast<double>((c + t - 1) / t * t) / c; };
+            const double w = waste(c0) * waste(c1);
+            if (w < best_w - 1e-9 || (w < best_w + 1e-9 && t > best_t)) {
+                best_w = w;
+                best_t = t;
+            }
+        }
+        const int T = best_t;
+        const int n_ta = (c0 + T - 1) / T, n_tb = (c1 + T - 1) / T;
+        const int64_t rest = st.n_out / (static_cast<int64_t>(c0) * c1);
+        const int64_t n_tiles = rest * n_ta * n_tb;
+        const int n_in = static_cast<int>(st.in.size());
+        if (n_tiles * (n_in + 2) > kTileTableMax) continue;
+        st.tile = T;
+        st.n_tiles = n_tiles;
+        st.tile_off_pos = static_cast<int64_t>(words->size());
+        std::vector<int64_t> off(n_in);
+        for (int64_t r = 0; r < rest; ++r) {
+            int64_t q = r;
+            std::fill(off.begin(), off.end(), 0);
+            for (int j = 2; j < n_axes; ++j) {
+                const int d = static_cast<int>(q % st.cards[j]);
+                q /= st.cards[j];
+                for (int i = 0; i < n_in; ++i) off[i] += static_cast<int64_t>(d) * st.in[i].strides[j];
+            }
+            for (int tb = 0; tb < n_tb; ++tb) {
+                for (int ta = 0; ta < n_ta; ++ta) {
+                    const int na = std::min(T, c0 - ta * T), nb = std::min(T, c1 - tb * T);
+                    words->push_back(static_cast<int32_t>(r * c0 * c1 + static_cast<int64_t>(tb) * T * c0 + ta * T));
+                    words->push_back(na | (nb << 8));
+                    for (int i = 0; i < n_in; ++i) {
+                        int64_t o = off[i];
+                        if (n_axes > 0) o += static_cast<int64_t>(ta) * T * st.in[i].strides[0];
+                        if (n_axes > 1) o += static_cast<int64_t>(tb) * T * st.in[i].strides[1];
+                        words->push_back(static_cast<int32_t>(o));
+                    }
+                }
+            }
+        }
+    }
+}
+
 void free_scratch(sbn_program *P) {
     if (P->exec) {
         cudaGraphExecDestroy(P->exec);
@@ -278,6 +348,8 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
             d.ev_card[k] = in.ev[k].card;
         }
         for (size_t j = 0; j < in.strides.size(); ++j) d.stride[j] = in.strides[j];
+        d.cls = ((!in.strides.empty() && in.strides[0] != 0) ? 1 : 0) |
+                ((in.strides.size() > 1 && in.strides[1] != 0) ? 2 : 0);
         d.smem_off = -1;
         d.stage_floats = 0;
         if (st.kind == 1 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
@@ -287,7 +359,21 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         }
     }
     q->smem_floats = smem;
-    if (st.kind == 1) {
+    if (st.kind == 1 && st.tile > 0 && P->use_tiled) {
+        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * kTiledV;
+        const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
+        // enough CTAs for ~4 waves (148 SMs x ~6 resident CTAs), otherwise as many
+        // consecutive tiles per CTA as possible (neighbouring tiles share operands in L1)
+        const int64_t target = 4 * 148 * 6;
+        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(st.n_tiles, target / std::max<int64_t>(1, n_rblocks)));
+        int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
+        q->tiles_per_cta = static_cast<int32_t>(tpc);
+        q->n_tiles = static_cast<int32_t>(st.n_tiles);
+        q->tile_off = P->d_tile_off + st.tile_off_pos;
+        q->n_bblocks = static_cast<int32_t>(n_rblocks);
+        q->tile1 = 0;
+        q->n_tile1 = 0;
+    } else if (st.kind == 1) {
         const int c0 = q->n_axes > 0 ? q->card[0] : 1;
         const int c1 = q->n_axes > 1 ? q->card[1] : 1;
         const int64_t n_bblocks = (n_rows + SBN_ROWS_PER_CTA - 1) / SBN_ROWS_PER_CTA;
@@ -350,8 +436,43 @@ cudaError_t set_smem_attr_n() {
     return e;
 }
 
+template <int N_IN>
+cudaError_t launch_tiled_n(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
+    const dim3 g(static_cast<unsigned>(grid)), b(SBN_TILED_THREADS);
+    switch (tile) {
+        case 2: sbn_step_tiled<N_IN, 2, kTiledV><<<g, b, smem, stream>>>(q); break;
+        case 3: sbn_step_tiled<N_IN, 3, kTiledV><<<g, b, smem, stream>>>(q); break;
+        case 4: sbn_step_tiled<N_IN, 4, kTiledV><<<g, b, smem, stream>>>(q); break;
+        case 5: sbn_step_tiled<N_IN, 5, kTiledV><<<g, b, smem, stream>>>(q); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int N_IN>
+cudaError_t set_tiled_attr_n() {
+    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 2, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 3, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 4, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 5, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    return e;
+}
+
 cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cudaStream_t stream) {
     P->launches++;
+    if (st.kind == 1 && q.tile_off != nullptr) {
+        const int64_t chunks = (q.n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+        const int64_t grid = chunks * q.n_bblocks;
+        if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
+        switch (q.n_in) {
+            case 1: return launch_tiled_n<1>(q, st.tile, grid, stream);
+            case 2: return launch_tiled_n<2>(q, st.tile, grid, stream);
+            case 3: return launch_tiled_n<3>(q, st.tile, grid, stream);
+            case 4: return launch_tiled_n<4>(q, st.tile, grid, stream);
+        }
+        return cudaErrorInvalidValue;
+    }
     if (st.kind == 0) {
         const int threads = 256;
         const int64_t grid = (st.n_out + threads - 1) / threads;
@@ -490,14 +611,34 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
                 off += round_up(s.padded, 64);
             }
     }
-    SBN_CUDA_P(set_smem_attr_n<1>());
-    SBN_CUDA_P(set_smem_attr_n<2>());
-    SBN_CUDA_P(set_smem_attr_n<3>());
-    SBN_CUDA_P(set_smem_attr_n<4>());
-    SBN_CUDA_P(set_smem_attr_n<5>());
-    SBN_CUDA_P(set_smem_attr_n<6>());
-    SBN_CUDA_P(set_smem_attr_n<7>());
-    SBN_CUDA_P(set_smem_attr_n<8>());
+    {
+        std::vector<int32_t> tile_words;
+        plan_tiles(P, &tile_words);
+        if (!tile_words.empty()) {
+            SBN_CUDA_P(cudaMalloc(&P->d_tile_off, tile_words.size() * 4));
+            SBN_CUDA_P(cudaMemcpy(P->d_tile_off, tile_words.data(), tile_words.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    {
+        // opt every step-kernel instantiation into SBN_SMEM_BUDGET of dynamic shared memory
+        // (once per device and process)
+        static bool done[64] = {false};
+        if (device < 64 && !done[device]) {
+            SBN_CUDA_P(set_smem_attr_n<1>());
+            SBN_CUDA_P(set_smem_attr_n<2>());
+            SBN_CUDA_P(set_smem_attr_n<3>());
+            SBN_CUDA_P(set_smem_attr_n<4>());
+            SBN_CUDA_P(set_smem_attr_n<5>());
+            SBN_CUDA_P(set_smem_attr_n<6>());
+            SBN_CUDA_P(set_smem_attr_n<7>());
+            SBN_CUDA_P(set_smem_attr_n<8>());
+            SBN_CUDA_P(set_tiled_attr_n<1>());
+            SBN_CUDA_P(set_tiled_attr_n<2>());
+            SBN_CUDA_P(set_tiled_attr_n<3>());
+            SBN_CUDA_P(set_tiled_attr_n<4>());
+            done[device] = true;
+        }
+    }
 #undef SBN_CUDA_P
     *out = P;
     return SBN_OK;
@@ -508,6 +649,7 @@ void sbn_program_destroy(sbn_program *P) {
     cudaSetDevice(P->device);
     free_scratch(P);
     cudaFree(P->d_shared);
+    cudaFree(P->d_tile_off);
     cudaFree(P->d_tables);
     if (P->stream) cudaStreamDestroy(P->stream);
     delete P;
@@ -670,6 +812,16 @@ int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
 int sbn_program_set_graph(sbn_program *P, int enabled) {
     if (!P) return fail(SBN_E_INVALID, "null program");
     P->use_graph = enabled != 0;
+    return SBN_OK;
+}
+
+int sbn_program_set_tiled(sbn_program *P, int enabled) {
+    if (!P) return fail(SBN_E_INVALID, "null program");
+    if (P->use_tiled != (enabled != 0) && P->exec) {
+        cudaGraphExecDestroy(P->exec);
+        P->exec = nullptr;
+    }
+    P->use_tiled = enabled != 0;
     return SBN_OK;
 }
 

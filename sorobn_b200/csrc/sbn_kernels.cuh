@@ -33,7 +33,7 @@ struct SbnInput {
     int32_t n_ev;                    // evidence axes gathered per row
     int32_t smem_off;                // float offset of the staged copy, -1 = read global
     int32_t stage_floats;            // floats copied by the bulk-TMA (multiple of 4)
-    int32_t pad_;
+    int32_t cls;                     // tiled kernel: 0 = lacks axes 0 and 1, 1 = has axis 0, 2 = axis 1, 3 = both
     int32_t ev_col[SBN_MAX_EV];
     int32_t ev_stride[SBN_MAX_EV];
     int32_t ev_card[SBN_MAX_EV];     // codes are clamped to card-1 (no out-of-bounds gather)
@@ -54,6 +54,9 @@ struct SbnStep {
     int32_t n_tile1;     // ceil(card[1] / tile1)
     int32_t n_bblocks;   // CTAs along the row axis
     int32_t smem_floats; // staged floats in total
+    int32_t tiles_per_cta;            // tiled kernel: consecutive tiles one CTA walks
+    const int32_t *tile_off;          // tiled kernel: [n_tiles][n_in + 2] = out entry, na | nb << 8, input offsets
+    int32_t n_tiles;
     int32_t pad_;
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
@@ -221,6 +224,210 @@ __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_con
             *reinterpret_cast<float4 *>(p.out + static_cast<int64_t>(o_rest + d1 * c0 + d0) * ld + b) = acc;
 #pragma unroll
             for (int i = 0; i < N_IN; ++i) e0[i] += p.n_axes > 0 ? p.in[i].stride[0] : 0;
+        }
+    }
+}
+
+
+// --------------------------------------------------------------- tiled step kernel
+// The fast path.  Same contract as sbn_step_batched, different blocking:
+//
+//   * tile = T digits of output axis 0 x T digits of axis 1 (one combination of the other
+//     axes), accumulated in registers for V = 2 consecutive evidence rows per thread;
+//   * every input is classed by which of the two tile axes it carries: a factor that lacks
+//     axis 0 is loaded once per tile column instead of once per output, one that lacks
+//     both once per tile -- the planner orders the axes to minimise these loads
+//     (planner.py `_tile_axes`), which turns the 2*cx loads per output of the naive loop
+//     into (T + T) * cx per T*T outputs for a product of two batched factors;
+//   * the mixed-radix decomposition of the tile index is row-invariant, so it is done
+//     once on the host: `tile_off` holds, per tile, the output entry and every input's
+//     element offset.  A CTA walks `tiles_per_cta` consecutive tiles for its 256 rows, so
+//     operands shared by neighbouring tiles are L1 hits;
+//   * tables (CPTs, evidence-independent factors) are staged in shared memory by bulk-TMA
+//     and gathered with the row's evidence offset.
+template <int V>
+struct SbnVec;
+template <>
+struct SbnVec<2> {
+    using type = float2;
+};
+template <>
+struct SbnVec<4> {
+    using type = float4;
+};
+
+template <int V>
+__device__ __forceinline__ void sbn_ldv(float (&r)[V], const float *ptr) {
+    const typename SbnVec<V>::type t = *reinterpret_cast<const typename SbnVec<V>::type *>(ptr);
+    memcpy(r, &t, sizeof t);
+}
+template <int V>
+__device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
+    typename SbnVec<V>::type t;
+    memcpy(&t, r, sizeof t);
+    *reinterpret_cast<typename SbnVec<V>::type *>(ptr) = t;
+}
+
+#define SBN_TILED_THREADS 128
+
+template <int N_IN, int T, int V>
+__global__ void __launch_bounds__(SBN_TILED_THREADS, 4) sbn_step_tiled(const __grid_constant__ SbnStep p) {
+    extern __shared__ __align__(16) float s_tab[];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const bool staged = p.smem_floats > 0;
+    if (staged) {
+        if (threadIdx.x == 0) {
+            sbn_mbar_init(&s_bar, 1);
+            sbn_fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sbn_mbar_expect_tx(&s_bar, static_cast<uint32_t>(p.smem_floats) * 4u);
+#pragma unroll
+            for (int i = 0; i < N_IN; ++i) {
+                if (p.in[i].smem_off >= 0) {
+                    sbn_tma_bulk_g2s(s_tab + p.in[i].smem_off, p.in[i].ptr,
+                                     static_cast<uint32_t>(p.in[i].stage_floats) * 4u, &s_bar);
+                }
+            }
+        }
+    }
+
+    const int rblock = blockIdx.x % p.n_bblocks;
+    const int chunk = blockIdx.x / p.n_bblocks;
+    const int b = (rblock * SBN_TILED_THREADS + threadIdx.x) * V;
+    const bool live = b < p.n_rows;  // b % V == 0 and ld % 32 == 0: the vector stays inside the pitch
+
+    // per-row evidence offsets of the gathered tables
+    int evo[N_IN][V];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) {
+#pragma unroll
+        for (int l = 0; l < V; ++l) evo[i][l] = 0;
+        if (!p.in[i].batched && live) {
+            for (int k = 0; k < p.in[i].n_ev; ++k) {
+                const uint8_t *col = p.ev + static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev + b;
+                const int s = p.in[i].ev_stride[k];
+                const int top = p.in[i].ev_card[k] - 1;
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    const int code = (b + l < p.n_rows) ? min(static_cast<int>(col[l]), top) : 0;
+                    evo[i][l] += code * s;
+                }
+            }
+        }
+    }
+
+    if (staged) sbn_mbar_wait(&s_bar, 0);
+    if (!live) return;
+
+    const int64_t ld = p.ld;
+    const int c0 = p.n_axes > 0 ? p.card[0] : 1;
+    const int t_begin = chunk * p.tiles_per_cta;
+    const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
+
+    // one value (V rows) of input i at element offset e
+    auto fetch = [&](int i, int e, float (&r)[V]) {
+        if (p.in[i].batched) {
+            sbn_ldv<V>(r, p.in[i].ptr + static_cast<int64_t>(e) * ld + b);
+        } else {
+            const float *t = s_tab + p.in[i].smem_off + e;
+#pragma unroll
+            for (int l = 0; l < V; ++l) r[l] = t[evo[i][l]];
+        }
+    };
+
+    for (int t = t_begin; t < t_end; ++t) {
+        const int32_t *row = p.tile_off + static_cast<int64_t>(t) * (N_IN + 2);
+        const int o_base = __ldg(row);
+        const int nab = __ldg(row + 1);
+        const int na = nab & 0xff, nb = nab >> 8;
+        int base[N_IN];
+#pragma unroll
+        for (int i = 0; i < N_IN; ++i) base[i] = __ldg(row + 2 + i);
+
+        float acc[T][T][V];
+#pragma unroll
+        for (int d0 = 0; d0 < T; ++d0)
+#pragma unroll
+            for (int d1 = 0; d1 < T; ++d1)
+#pragma unroll
+                for (int l = 0; l < V; ++l) acc[d0][d1][l] = 0.f;
+
+        for (int x = 0; x < p.cx; ++x) {
+            float u[V], a[T][V], bb[T][V];
+#pragma unroll
+            for (int l = 0; l < V; ++l) u[l] = 1.f;
+#pragma unroll
+            for (int d = 0; d < T; ++d)
+#pragma unroll
+                for (int l = 0; l < V; ++l) a[d][l] = bb[d][l] = 1.f;
+
+#pragma unroll
+            for (int i = 0; i < N_IN; ++i) {
+                const int e = base[i] + x * p.in[i].sx;
+                const int cls = p.in[i].cls;
+                if (cls == 0) {
+                    float r[V];
+                    fetch(i, e, r);
+#pragma unroll
+                    for (int l = 0; l < V; ++l) u[l] *= r[l];
+                } else if (cls == 1) {
+                    const int s0 = p.in[i].stride[0];
+#pragma unroll
+                    for (int d0 = 0; d0 < T; ++d0) {
+                        if (d0 < na) {
+                            float r[V];
+                            fetch(i, e + d0 * s0, r);
+#pragma unroll
+                            for (int l = 0; l < V; ++l) a[d0][l] *= r[l];
+                        }
+                    }
+                } else if (cls == 2) {
+                    const int s1 = p.in[i].stride[1];
+#pragma unroll
+                    for (int d1 = 0; d1 < T; ++d1) {
+                        if (d1 < nb) {
+                            float r[V];
+                            fetch(i, e + d1 * s1, r);
+#pragma unroll
+                            for (int l = 0; l < V; ++l) bb[d1][l] *= r[l];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d0 = 0; d0 < T; ++d0) {
+#pragma unroll
+                for (int d1 = 0; d1 < T; ++d1) {
+                    if (d0 < na && d1 < nb) {
+                        float w[V];
+#pragma unroll
+                        for (int l = 0; l < V; ++l) w[l] = u[l] * a[d0][l] * bb[d1][l];
+#pragma unroll
+                        for (int i = 0; i < N_IN; ++i) {
+                            if (p.in[i].cls == 3) {
+                                float r[V];
+                                fetch(i, base[i] + x * p.in[i].sx + d0 * p.in[i].stride[0] + d1 * p.in[i].stride[1], r);
+#pragma unroll
+                                for (int l = 0; l < V; ++l) w[l] *= r[l];
+                            }
+                        }
+#pragma unroll
+                        for (int l = 0; l < V; ++l) acc[d0][d1][l] += w[l];
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int d1 = 0; d1 < T; ++d1) {
+#pragma unroll
+            for (int d0 = 0; d0 < T; ++d0) {
+                if (d0 < na && d1 < nb)
+                    sbn_stv<V>(p.out + static_cast<int64_t>(o_base + d1 * c0 + d0) * ld + b, acc[d0][d1]);
+            }
         }
     }
 }

@@ -63,6 +63,8 @@ def load():
     lib.sbn_program_info.argtypes = [vp, vp, i64]
     lib.sbn_program_set_graph.restype = i32
     lib.sbn_program_set_graph.argtypes = [vp, i32]
+    lib.sbn_program_set_tiled.restype = i32
+    lib.sbn_program_set_tiled.argtypes = [vp, i32]
     lib.sbn_host_alloc.restype = i32
     lib.sbn_host_alloc.argtypes = [c.POINTER(vp), i64]
     lib.sbn_host_free.restype = i32
@@ -76,7 +78,7 @@ def load():
 EXPORTS = (
     "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
-    "sbn_program_info", "sbn_program_set_graph", "sbn_host_alloc", "sbn_host_free",
+    "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_host_alloc", "sbn_host_free",
 )
 
 
@@ -153,6 +155,9 @@ class Program:
 
     def set_graph(self, enabled: bool):
         _check(load().sbn_program_set_graph(self._h, int(bool(enabled))))
+
+    def set_tiled(self, enabled: bool):
+        _check(load().sbn_program_set_tiled(self._h, int(bool(enabled))))
 
     def info(self) -> dict:
         buf = (ctypes.c_int64 * 8)()

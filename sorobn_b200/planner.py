@@ -47,6 +47,7 @@ VERSION = 3
 MAX_IN = 8  # factors fused per launch (csrc/sbn_kernels.cuh: SBN_MAX_IN)
 MAX_AXES = 20  # output axes per step (SBN_MAX_AXES)
 MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
+TILE_EDGE = 5  # largest register-tile edge of sbn_step_tiled
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
@@ -210,15 +211,16 @@ def _min_fill_order(scopes, hidden, card):
 
 
 def table_scale_log2(table: np.ndarray) -> int:
-    """Power-of-two exponent k such that table * 2**k has geometric mean ~1 over
-    its positive entries.  Scaling a CPT by a constant cancels in the final
-    normalisation (bayes_net.py:790) and a power of two is exact in fp32; it keeps
-    products of ~100 probabilities away from fp32 underflow."""
-    pos = table[table > 0]
-    if pos.size == 0:
-        return 0
-    k = -int(np.round(np.mean(np.log2(pos))))
-    return int(np.clip(k, -60, 60))
+    """Power-of-two exponent applied to a CPT before it is shipped (always 0 today).
+
+    CPTs are shipped as plain probabilities: then every intermediate factor entry is
+    <= 1 (when a variable is eliminated its own CPT, which sums to one over it, is in
+    the product and every other entry is <= 1 by induction), so fp32 can never
+    overflow.  What can happen is underflow when the evidence is astronomically
+    unlikely (P(event) < ~1e-24); the engine detects that per row from the normaliser
+    (DESIGN.md "fp32 range").  The hook stays because a per-table power of two is exact
+    and cancels in the normalisation (bayes_net.py:790)."""
+    return 0
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN) -> Plan:
@@ -319,14 +321,35 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         return int(np.prod([card[u] for u in f.vars], dtype=np.int64)) if f.vars else 1
 
     def axis_order(inputs, out_set):
-        """Fastest-first order of the output axes.  Axes that the largest batched
-        input does not have go first (its entries are then re-used by consecutive
-        outputs, which the kernel's o-tile keeps in registers/L1); the rest follow
-        that input's own order so its reads stay sequential."""
+        """Fastest-first order of the output axes (`_tile_axes` in the kernel docs).
+
+        Axes 0 and 1 span the register tile of csrc/sbn_step_tiled: an input that lacks
+        axis 0 is loaded once per tile column, one that lacks both once per tile.  Every
+        ordered pair of output axes is scored by the loads per output it implies
+        (batched inputs weigh double: they come from L1/L2/HBM, tables from shared
+        memory) and the cheapest pair wins; the remaining axes follow the largest
+        batched input's own order so that its reads stay sequential."""
+        out = sorted(out_set)
         big = max(inputs, key=lambda f: (f.batched, fsize(f)))
-        in_big = [u for _, u in sorted(zip(big.strides, big.vars)) if u in out_set]
-        new = sorted(u for u in out_set if u not in big.vars)
-        return new + in_big
+        tail = [u for _, u in sorted(zip(big.strides, big.vars)) if u in out_set]
+        tail += [u for u in out if u not in big.vars]
+        if len(out) < 2:
+            return out
+        best_key, best = None, None
+        for a0 in out:
+            t0 = min(int(card[a0]), TILE_EDGE)
+            for a1 in out:
+                if a1 == a0:
+                    continue
+                t1 = min(int(card[a1]), TILE_EDGE)
+                loads = 0.0
+                for f in inputs:
+                    n = (t0 if a0 in f.vars else 1) * (t1 if a1 in f.vars else 1)
+                    loads += n * (2.0 if f.batched else 1.0)
+                key = (loads / (t0 * t1), -(t0 * t1), a0, a1)
+                if best_key is None or key < best_key:
+                    best_key, best = key, (a0, a1)
+        return [best[0], best[1]] + [u for u in tail if u not in best]
 
     def product_chain(inputs, elim, final_vars=None):
         inputs = list(inputs)

@@ -73,15 +73,17 @@ def grid(rows: int, cols: int, n_states: int, seed: int = 0, alpha: float = 1.0)
     return NetSpec(f"grid{rows}x{cols}s{n_states}", nodes, parents, cards, cpt)
 
 
-def random_dag(n_nodes: int, max_parents: int, n_states: int, seed: int = 0, alpha: float = 1.0,
+def random_dag(n_nodes: int, max_parents: int, n_states, seed: int = 0, alpha: float = 1.0,
                window: int | None = None) -> NetSpec:
     """Random DAG: node k draws 0..max_parents parents among the `window` nodes
     before it (all earlier nodes when window is None).  A finite window keeps the
-    induced width bounded, like the banded structure of real diagnostic networks."""
+    induced width bounded, like the banded structure of real diagnostic networks.
+    `n_states` is one cardinality for every node or a sequence cycled over the nodes."""
     rng = np.random.default_rng(seed)
     width = len(str(n_nodes - 1))
     nodes = [f"v{k:0{width}d}" for k in range(n_nodes)]
-    parents, cards, cpt = {}, {n: n_states for n in nodes}, {}
+    states = [n_states] * n_nodes if isinstance(n_states, int) else [n_states[k % len(n_states)] for k in range(n_nodes)]
+    parents, cards, cpt = {}, {n: int(c) for n, c in zip(nodes, states)}, {}
     for k, n in enumerate(nodes):
         lo = 0 if window is None else max(0, k - window)
         pool = nodes[lo:k]
@@ -92,7 +94,8 @@ def random_dag(n_nodes: int, max_parents: int, n_states: int, seed: int = 0, alp
             parents[n] = ps
     for n in nodes:
         cpt[n] = _random_cpt(rng, [cards[p] for p in parents.get(n, [])], cards[n], alpha)
-    return NetSpec(f"dag{n_nodes}p{max_parents}s{n_states}", nodes, parents, cards, cpt)
+    tag = n_states if isinstance(n_states, int) else "x".join(map(str, n_states))
+    return NetSpec(f"dag{n_nodes}p{max_parents}s{tag}", nodes, parents, cards, cpt)
 
 
 def chain(n_nodes: int, n_states: int, seed: int = 0) -> NetSpec:

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path with the reference (golden vectors) and the oracle.
+
+Every test here calls through the C ABI (ctypes -> libsorobn_b200.so).  Tolerance:
+1e-6 relative on every posterior entry (BASELINE.json's north_star); the arithmetic is
+fp32 on the device against float64 in the reference.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import build_network, case_event, dense_answer, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    want = np.asarray(want, dtype=np.float64).reshape(-1)
+    mask = want > 0
+    err = 0.0
+    if mask.any():
+        err = float(np.max(np.abs(got[mask] - want[mask]) / want[mask]))
+    if (~mask).any():
+        err = max(err, float(np.max(np.abs(got[~mask]))))  # exact zeros must stay zero
+    return err
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_query_matches_reference_goldens(name):
+    """BayesNet.query (flat kernels, one event) against the reference's own answers:
+    same index (zero rows dropped), same values."""
+    golden = load_golden(name)
+    bn = build_network(golden)
+    worst = 0.0
+    for case in golden["cases"]:
+        ans = bn.query(*case["query"], event=case_event(case))
+        assert list(ans.index.names) == case["names"]
+        got_idx = [list(k) if isinstance(k, tuple) else [k] for k in ans.index.tolist()]
+        assert got_idx == case["index"], (case["query"], case["event"])
+        assert ans.name == f"P({', '.join(case['query'])})"
+        if case["values"]:
+            worst = max(worst, rel_err(ans.to_numpy(), case["values"]))
+    assert worst < RTOL, worst
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_query_many_matches_reference_goldens(name):
+    """The batched kernels on the same cases: golden cases that share (query, evidence
+    variables) are answered together as one batch."""
+    golden = load_golden(name)
+    bn = build_network(golden)
+    net = bn._compiled
+    groups = {}
+    for case in golden["cases"]:
+        key = (tuple(case["query"]), tuple(k for k, _ in case["event"]))
+        groups.setdefault(key, []).append(case)
+    worst = 0.0
+    for (query, ev_vars), cases in groups.items():
+        events = pd.DataFrame([case_event(c) for c in cases], columns=list(ev_vars))
+        got = bn.query_many(*query, events=events)
+        assert got.shape[0] == len(cases)
+        domains = {n: net.domains[net.index[n]] for n in cases[0]["names"]}
+        for row, case in zip(got.to_numpy(), cases):
+            want = dense_answer(case, domains).reshape(-1)
+            if not case["values"]:  # impossible evidence: reference returns an empty Series
+                assert np.isnan(row).all()
+                continue
+            worst = max(worst, rel_err(row, want))
+    assert worst < RTOL, worst
+
+
+def test_reference_doctests_on_device():
+    from sorobn_b200 import examples
+
+    bn = examples.sprinkler()
+    assert np.allclose(bn.query("Rain", event={"Sprinkler": True}).to_numpy(), [0.7, 0.3], rtol=RTOL)
+    bn = examples.asia()
+    ans = bn.query("Lung cancer", "Tuberculosis", event={"Visit to Asia": True, "Smoker": True})
+    assert ans.index.names == ["Lung cancer", "Tuberculosis"]
+    assert np.allclose(ans.to_numpy(), [0.855, 0.045, 0.095, 0.005], rtol=RTOL)
+    assert np.allclose(bn.query("Lung cancer", event={"Visit to Asia": True, "Smoker": False}).to_numpy(),
+                       [0.99, 0.01], rtol=RTOL)
+    bn = examples.alarm()
+    ans = bn.query("John calls", "Mary calls", event={"Burglary": True, "Earthquake": False})
+    assert np.allclose(ans.to_numpy(), [0.08463, 0.06637, 0.25677, 0.59223], rtol=1e-5)
+    # BASELINE.json configs[0]
+    ans = bn.query("Burglary", event={"John calls": True, "Mary calls": True})
+    assert np.allclose(ans.to_numpy(), [0.715828, 0.284172], atol=1e-6)
+    bn = examples.grades()
+    ans = bn.query("Letter", "SAT", event={"Intelligence": "Smart"})
+    assert np.allclose(ans.to_numpy(), [0.153544, 0.614176, 0.046456, 0.185824], atol=1e-6)
+
+
+def test_independent_variables_and_no_evidence():
+    # reference test_indep_vars (test_bayes_net.py:121-165)
+    from sorobn_b200 import BayesNet
+
+    bn = BayesNet("A", "B")
+    bn.P["A"] = pd.Series({1: 0.2, 2: 0.3, 3: 0.5})
+    bn.P["B"] = pd.Series({1: 0.4, 2: 0.2, 3: 0.4})
+    bn.prepare()
+    for b in (1, 2, 3):
+        ans = bn.query("A", event={"B": b})
+        assert ans.index.tolist() == [1, 2, 3]
+        assert np.allclose(ans.to_numpy(), [0.2, 0.3, 0.5], rtol=RTOL)
+    assert np.allclose(bn.query("A", event={}).to_numpy(), [0.2, 0.3, 0.5], rtol=RTOL)
+    many = bn.query_many("B", events=pd.DataFrame({"A": [1, 3, 2, 1, 1]}))
+    assert np.allclose(many.to_numpy(), np.tile([0.4, 0.2, 0.4], (5, 1)), rtol=RTOL)
+
+
+def test_cpt_forms_and_impute():
+    # reference test_cpt_with_index_names / test_cpt_dataframe (test_bayes_net.py:168-233)
+    from sorobn_b200 import BayesNet, examples
+
+    bn = BayesNet(("A", "C"), ("B", "C"))
+    bn.P["A"] = pd.Series({True: 0.7, False: 0.3})
+    bn.P["B"] = pd.Series({True: 0.4, False: 0.6})
+    pc = pd.DataFrame({
+        "B": [True, True, True, True, False, False, False, False],
+        "A": [True, True, False, False, True, True, False, False],
+        "C": [True, False, True, False, True, False, True, False],
+        "p": [1, 0, 0, 1, 0.5, 0.5, 0.001, 0.999],
+    })
+    bn.P["C"] = pc.set_index(["B", "A", "C"])["p"]
+    bn.prepare()
+    pd.testing.assert_series_equal(
+        bn.query("C", event={"B": False, "A": True}),
+        pd.Series([0.5, 0.5], name="P(C)", index=pd.Index([False, True], name="C")),
+        rtol=RTOL,
+    )
+    # impute (bayes_net.py:877-908)
+    bn = examples.asia()
+    sample = {"Smoker": True, "Dispnea": True, "Lung cancer": None, "Bronchitis": None}
+    filled = bn.impute(sample)
+    post = bn.query("Lung cancer", "Bronchitis", event={"Smoker": True, "Dispnea": True})
+    best = post.idxmax()
+    assert filled["Bronchitis"] == best[0] and filled["Lung cancer"] == best[1]
+    assert filled["Smoker"] is True or filled["Smoker"] == True  # noqa: E712
+
+
+def test_impossible_and_unknown_evidence():
+    from sorobn_b200 import examples
+
+    bn = examples.asia()
+    # P(TB or cancer = False, Lung cancer = True) == 0: the reference returns an empty Series
+    ans = bn.query("Smoker", event={"TB or cancer": False, "Lung cancer": True})
+    assert len(ans) == 0
+    ans = bn.query("Smoker", event={"Dispnea": "maybe"})
+    assert len(ans) == 0
+    many = bn.query_many("Smoker", events=pd.DataFrame({"TB or cancer": [False, True], "Lung cancer": [True, True]}))
+    assert np.isnan(many.iloc[0]).all() and np.isclose(many.iloc[1].sum(), 1.0)
+
+
+@pytest.mark.parametrize("n_rows", [1, 3, 4, 5, 31, 32, 33, 511, 512, 513, 1027])
+def test_ragged_batch_sizes(n_rows):
+    """Row counts around the float4 / warp / CTA boundaries."""
+    from oracle import ve_oracle
+    from sorobn_b200 import workloads
+
+    wl = workloads.asia_1m()
+    bn = wl.build()
+    events = wl.events(n_rows, seed=n_rows, bn=bn)
+    got = bn.query_many(*wl.query, events=events).to_numpy()
+    net = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    cache = {}
+    for b in range(n_rows):
+        key = tuple(events.iloc[b])
+        if key not in cache:
+            cache[key] = ve_oracle.query(net, *wl.query, event=dict(zip(wl.evidence, key)))[1].reshape(-1)
+        assert rel_err(got[b], cache[key]) < RTOL
+
+
+def test_random_networks_batched_vs_oracle():
+    """Random DAGs with mixed cardinalities, random query / evidence sets."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet, synthetic
+
+    rng = np.random.default_rng(2024)
+    worst = 0.0
+    for trial in range(12):
+        n = int(rng.integers(4, 14))
+        spec = synthetic.random_dag(n, 3, int(rng.integers(2, 5)), seed=100 + trial)
+        bn = synthetic.load(spec, BayesNet)
+        net = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+        perm = rng.permutation(n)
+        nq = int(rng.integers(1, 3))
+        ne = int(rng.integers(0, n - nq))
+        query = [spec.nodes[i] for i in perm[:nq]]
+        evs = [spec.nodes[i] for i in perm[nq:nq + ne]]
+        B = 70
+        events = synthetic.random_events(spec, evs, B, seed=trial)
+        got = bn.query_many(*query, events=events).to_numpy()
+        for b in range(0, B, 7):
+            ev = {v: int(events[v].iloc[b]) for v in evs}
+            want = ve_oracle.query(net, *query, event=ev)[1].reshape(-1)
+            worst = max(worst, rel_err(got[b], want))
+    assert worst < RTOL, worst
+
+
+@pytest.mark.parametrize("cards", [2, 3, 4, 5, 6, 7, 8, (2, 5, 3), (8, 2, 4, 3), (5, 7)])
+def test_tiled_and_plain_kernels_agree_with_oracle(cards):
+    """Every tile edge of sbn_step_tiled (2..5, with partial tiles for 6, 7, 8 states) and
+    the plain sbn_step_batched kernel, on the same programs, against the oracle."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet, engine, planner, synthetic
+
+    rng = np.random.default_rng(hash(str(cards)) % 2**32)
+    worst = 0.0
+    for trial in range(3):
+        spec = synthetic.random_dag(14, 3, cards, seed=40 + trial, window=5)
+        bn = synthetic.load(spec, BayesNet)
+        net = bn._compiled
+        dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+        perm = rng.permutation(14)
+        query = [spec.nodes[i] for i in perm[:1 + trial % 2]]
+        evs = [spec.nodes[i] for i in perm[2:2 + 3 + trial]]
+        plan = planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evs])
+        B = 301
+        events = synthetic.random_events(spec, evs, B, seed=trial)
+        codes = np.stack([events[v].to_numpy().astype(np.uint8) for v in evs])
+        prog = engine.Program(plan)
+        tiled = prog.run(codes, B).copy()
+        prog.set_tiled(False)
+        plain = prog.run(codes, B).copy()
+        assert np.allclose(tiled, plain, rtol=5e-6, atol=1e-30)
+        order = [net.names[v] for v in plan.order]
+        for b in range(0, B, 29):
+            ev = {v: int(events[v].iloc[b]) for v in evs}
+            want = ve_oracle.query(dn, *query, event=ev, order=order)[1].reshape(-1)
+            worst = max(worst, rel_err(tiled[:, b], want), rel_err(plain[:, b], want))
+    assert worst < RTOL, worst
+
+
+def test_full_size_grid_properties():
+    """BASELINE.json configs[2] at full size (10x10 grid, 5 states, 100k rows):
+    size-independent properties + an oracle sample."""
+    from oracle import ve_oracle
+    from sorobn_b200 import planner, workloads
+    from sorobn_b200 import engine
+
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    B = 100_000
+    codes = wl.codes(bn, B, seed=5)
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    prog = engine.Program(plan)
+    out = prog.run(codes, B)
+    assert out.shape == (5, B)
+    assert np.isfinite(out).all() and (out >= 0).all()
+    # every posterior sums to one
+    assert np.allclose(out.sum(axis=0), 1.0, atol=2e-6)
+    # determinism: same call, same bits
+    again = prog.run(codes, B)
+    assert np.array_equal(out, again)
+    # permutation equivariance: shuffled evidence rows give shuffled posteriors (bitwise)
+    perm = np.random.default_rng(0).permutation(B)
+    shuffled = prog.run(np.ascontiguousarray(codes[:, perm]), B)
+    assert np.array_equal(shuffled, out[:, perm])
+    # chunking invariance: a second program restricted to 4096-row chunks agrees bitwise
+    small = engine.Program(plan)
+    small.reserve(4096)
+    assert np.array_equal(small.run(codes, B), out)
+    # oracle on a sample of rows
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    order = [net.names[v] for v in plan.order]
+    worst = 0.0
+    for b in range(0, B, B // 16):
+        ev = {v: int(net.domains[net.index[v]][codes[i, b]]) for i, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        worst = max(worst, rel_err(out[:, b], want))
+    assert worst < RTOL, worst
+
+
+def test_device_pointer_api_matches_host_api():
+    """sbn_program_run_device on caller-owned device buffers (torch as the allocator)."""
+    import torch
+
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.asia_1m()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    prog = engine.Program(plan)
+    B = 10_007
+    codes = wl.codes(bn, B, seed=3)
+    want = prog.run(codes, B)
+    d_ev = torch.from_numpy(codes).cuda()
+    d_out = torch.full((prog.Q, B), -1.0, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for use_graph in (True, False, True):
+        prog.set_graph(use_graph)
+        d_out.fill_(-1.0)
+        prog.run_device(d_ev.data_ptr(), B, B, d_out.data_ptr(), B, stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    info = prog.info()
+    assert info["launches"] > 0 and info["Q"] == 2 and info["n_ev"] == 4

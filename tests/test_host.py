@@ -1,0 +1,203 @@
+"""Host-side logic of the BayesNet mirror (no GPU needed) and the C-ABI library's
+loadability.  Mirrors the reference's own tests (/root/reference/sorobn/test_bayes_net.py)
+where they concern the exact-inference path."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from sorobn_b200 import BayesNet, engine, examples
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def naive():
+    bn = BayesNet("A", "B", "C")
+    bn.P["A"] = pd.Series({True: 0.1, False: 0.9})
+    bn.P["B"] = pd.Series({True: 0.3, False: 0.7})
+    bn.P["C"] = pd.Series({True: 0.5, False: 0.5})
+    bn.prepare()
+    return bn
+
+
+ALL = [examples.alarm, examples.asia, examples.sprinkler, examples.grades, naive]
+
+
+@pytest.mark.parametrize("make", ALL, ids=lambda f: f.__name__)
+def test_check_Ps(make):
+    # reference check_Ps (test_bayes_net.py:52-63)
+    bn = make()
+    for child, parents in bn.parents.items():
+        P = bn.P[child]
+        assert P.index.names[-1] == child
+        assert P.index.names[:-1] == parents
+        assert np.allclose(P.groupby(parents).sum(), 1)
+    for orphan in set(bn.nodes) - set(bn.parents):
+        P = bn.P[orphan]
+        assert P.index.name == orphan
+        assert np.isclose(P.sum(), 1)
+
+
+def test_structure_matches_reference_doctests():
+    bn = examples.grades()
+    # examples.py:257-264
+    assert bn.nodes == ["Difficulty", "Intelligence", "Grade", "SAT", "Letter"]
+    assert bn.children == {"Difficulty": ["Grade"], "Intelligence": ["Grade", "SAT"], "Grade": ["Letter"]}
+    assert bn.parents == {"Grade": ["Difficulty", "Intelligence"], "SAT": ["Intelligence"], "Letter": ["Grade"]}
+    # bayes_net.py:987-998
+    assert BayesNet(("a", "b"), ("a", "c")).is_tree
+    assert not BayesNet(("a", "c"), ("b", "c")).is_tree
+    # bayes_net.py:1015-1031
+    bn = BayesNet((0, 3), (1, 4), (2, 5), (3, 6), (4, 6), (5, 8), (6, 8), (6, 9), (7, 9), (7, 10), (8, 11), (8, 12))
+    assert bn.markov_boundary(6) == [3, 4, 5, 7, 8, 9]
+    # bayes_net.py:1049-1060
+    assert list(examples.asia().iter_dfs()) == [
+        "Smoker", "Bronchitis", "Dispnea", "Lung cancer", "TB or cancer", "Positive X-ray", "Visit to Asia",
+        "Tuberculosis"]
+    bn = examples.asia()
+    assert bn.roots == ["Smoker", "Visit to Asia"]
+    assert set(bn.leaves) == {"Dispnea", "Positive X-ray"}
+    assert bn.ancestors("Dispnea") == {"Bronchitis", "Smoker", "TB or cancer", "Lung cancer", "Tuberculosis",
+                                       "Visit to Asia"}
+
+
+def test_structure_grammar_with_lists_and_cycles():
+    import graphlib
+
+    bn = BayesNet(("Smoker", ["Lung cancer", "Bronchitis"]), (["Tuberculosis", "Lung cancer"], "TB or cancer"))
+    assert bn.parents["TB or cancer"] == ["Lung cancer", "Tuberculosis"]
+    assert bn.children["Smoker"] == ["Bronchitis", "Lung cancer"]
+    with pytest.raises(graphlib.CycleError):
+        BayesNet(("a", "b"), ("b", "c"), ("c", "a"))
+
+
+def test_cpt_dataframe_forms():
+    # test_bayes_net.py:204-262
+    def make(cols):
+        bn = BayesNet(("A", "C"), ("B", "C"))
+        bn.P["A"] = pd.Series({True: 0.7, False: 0.3})
+        bn.P["B"] = pd.Series({True: 0.4, False: 0.6})
+        data = {
+            "A": [True, True, False, False],
+            "B": [True, False, True, False],
+            "C": [True, True, True, True],
+            "p": [0.9, 0.8, 0.7, 0.1],
+        }
+        bn.P["C"] = pd.DataFrame({c: data[c] for c in cols})
+        bn.prepare()
+        return bn
+
+    b1, b2 = make(["A", "B", "C", "p"]), make(["B", "C", "A", "p"])
+    pd.testing.assert_series_equal(b1.P["C"], b2.P["C"])
+    assert b1.P["C"].index.names == ["A", "B", "C"]
+    assert b1.P["C"].name == "P(C | A, B)" and b1.P["A"].name == "P(A)"
+
+
+def test_cpt_dataframe_errors():
+    # test_bayes_net.py:265-295
+    bn = BayesNet(("A", "B"))
+    bn.P["A"] = pd.Series({True: 0.5, False: 0.5})
+    bn.P["B"] = pd.DataFrame({"A": [True, True, False, False], "B": [True, False, True, False],
+                              "prob": [0.9, 0.1, 0.4, 0.6]})
+    with pytest.raises(ValueError, match="must have a 'p' column"):
+        bn.prepare()
+    bn.P["B"] = pd.DataFrame({"A": [True, True, False, False], "X": [True, False, True, False],
+                              "p": [0.9, 0.1, 0.4, 0.6]})
+    with pytest.raises(ValueError, match="has columns"):
+        bn.prepare()
+
+
+def test_compiled_tables_follow_sorted_domains():
+    bn = examples.grades()
+    net = bn._compiled
+    g = net.index["Grade"]
+    assert net.domains[g] == ["A", "B", "C"]
+    assert [net.names[p] for p in net.parents[g]] == ["Difficulty", "Intelligence"]
+    # P(Grade | Difficulty=Hard, Intelligence=Smart) = (.5, .3, .2)
+    assert np.allclose(net.cpt[g][1, 1], [0.5, 0.3, 0.2])
+    # string states
+    bn = BayesNet(("Weather", "Mood"))
+    bn.P["Weather"] = pd.Series({"Sunny": 0.7, "Rainy": 0.3})
+    bn.P["Mood"] = pd.DataFrame({"Weather": ["Sunny", "Sunny", "Rainy", "Rainy"],
+                                 "Mood": ["Happy", "Sad", "Happy", "Sad"], "p": [0.9, 0.1, 0.4, 0.6]})
+    bn.prepare()
+    net = bn._compiled
+    assert net.domains[net.index["Weather"]] == ["Rainy", "Sunny"]
+    assert np.allclose(net.cpt[net.index["Mood"]], [[0.4, 0.6], [0.9, 0.1]])
+
+
+def test_query_argument_errors_do_not_need_a_gpu():
+    bn = examples.alarm()
+    with pytest.raises(ValueError, match="At least one query variable"):
+        bn.query(event={})
+    with pytest.raises(ValueError, match="cannot be part of the event"):
+        bn.query("Alarm", event={"Alarm": True})
+    with pytest.raises(ValueError, match="Unknown algorithm"):
+        bn.query("Alarm", event={}, algorithm="magic")
+    with pytest.raises(NotImplementedError):
+        bn.query("Alarm", event={}, algorithm="gibbs")
+
+
+def test_no_silent_cpu_fallback():
+    """Without a GPU the exact path must fail loudly, not compute on the CPU."""
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    bn = examples.alarm()
+    with pytest.raises(engine.EngineError):
+        bn.query("Burglary", event={"John calls": True, "Mary calls": True})
+    with pytest.raises(engine.EngineError):
+        bn.query_many("Burglary", events=pd.DataFrame({"John calls": [True], "Mary calls": [False]}))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = engine.load()
+    assert lib.sbn_abi_version() == engine.ABI_VERSION
+    header = open(os.path.join(ROOT, "include", "sorobn_b200.h")).read()
+    declared = set(re.findall(r"\b(sbn_[a-z_]+)\s*\(", header))
+    assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
+    raw = ctypes.CDLL(engine.lib_path())
+    for name in declared:
+        assert hasattr(raw, name), name
+    m = re.search(r"#define SBN_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == lib.sbn_abi_version()
+
+
+def test_program_validation_rejects_malformed_programs():
+    """sbn_program_create parses and bounds-checks before touching the GPU."""
+    from sorobn_b200 import planner
+
+    lib = engine.load()
+    bn = examples.alarm()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index["Burglary"]], [net.index["John calls"]])
+    blob = np.ascontiguousarray(plan.table_blob)
+
+    def create(words):
+        h = ctypes.c_void_p()
+        w = np.ascontiguousarray(words, dtype=np.int32)
+        rc = lib.sbn_program_create(0, w.ctypes.data, w.size, blob.ctypes.data, blob.size, ctypes.byref(h))
+        msg = lib.sbn_last_error().decode()
+        if rc == 0:
+            lib.sbn_program_destroy(h)
+        return rc, msg
+
+    bad = plan.words.copy()
+    bad[0] = 123
+    assert create(bad)[0] == -1 and "magic" in create(bad)[1]
+    bad = plan.words.copy()
+    bad[1] = 99
+    assert create(bad)[0] == -1
+    assert create(plan.words[:-1])[0] == -1  # truncated
+    assert create(np.concatenate([plan.words, [0]]))[0] == -1  # trailing
+    hdr, tables, slots, steps = __import__("oracle.program_interp", fromlist=["parse"]).parse(plan.words)
+    # corrupt a stride so that an input would read past its table
+    bad = plan.words.copy()
+    bad[-1] = 10_000
+    rc, msg = create(bad)
+    assert rc == -1 and "past its buffer" in msg
+    # a well-formed program fails only because there is no device here (or succeeds on a GPU box)
+    rc, msg = create(plan.words)
+    assert rc in (0, -4), msg

@@ -1,0 +1,163 @@
+"""Planner + flat-program layout, checked on the CPU.
+
+`oracle/program_interp.py` executes the serialised int32 program word by word with
+numpy (the same words csrc/sbn_api.cu parses), so a pass here means the strides,
+evidence gathers, slot reuse and axis orders the device will see are right; the
+result must equal oracle.ve_oracle.query (bayes_net.py:739-794 restated) row by row.
+"""
+import numpy as np
+import pytest
+
+from oracle import program_interp, ve_oracle
+from sorobn_b200 import BayesNet, examples, planner, synthetic, workloads
+
+
+def run_plan(bn, query, ev_vars, codes, mode, **kw):
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in ev_vars], mode=mode, **kw)
+    n = codes.shape[1] if codes.size else (1 if mode == planner.MODE_FLAT else 3)
+    return plan, program_interp.run(plan.words, plan.table_blob64, codes, n_rows=n)
+
+
+def oracle_rows(bn, query, ev_vars, codes):
+    net = bn._compiled
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    out = []
+    for b in range(codes.shape[1]):
+        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(ev_vars)}
+        out.append(ve_oracle.query(dn, *query, event=ev)[1].reshape(-1))
+    return np.stack(out, axis=1)
+
+
+@pytest.mark.parametrize("trial", range(25))
+def test_random_networks_batched_and_flat(trial):
+    rng = np.random.default_rng(trial)
+    n = int(rng.integers(3, 13))
+    spec = synthetic.random_dag(n, 3, int(rng.integers(2, 5)), seed=trial)
+    bn = synthetic.load(spec, BayesNet)
+    perm = rng.permutation(n)
+    nq = int(rng.integers(1, 3))
+    ne = int(rng.integers(0, n - nq))
+    query = [spec.nodes[i] for i in perm[:nq]]
+    evs = [spec.nodes[i] for i in perm[nq:nq + ne]]
+    B = 6
+    events = synthetic.random_events(spec, evs, B, seed=trial)
+    codes = np.stack([events[v].to_numpy().astype(np.uint8) for v in evs]) if evs else np.zeros((0, B), np.uint8)
+    want = oracle_rows(bn, query, evs, codes) if evs else None
+    plan, got = run_plan(bn, query, evs, codes, planner.MODE_BATCHED)
+    if evs:
+        assert np.allclose(got, want, rtol=1e-12, atol=0)
+        for b in range(B):
+            _, flat = run_plan(bn, query, evs, codes[:, b:b + 1], planner.MODE_FLAT)
+            assert np.allclose(flat[:, 0], want[:, b], rtol=1e-12, atol=0)
+    else:
+        net = bn._compiled
+        dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+        ref = ve_oracle.query(dn, *query, event={})[1].reshape(-1)
+        assert np.allclose(got, ref[:, None], rtol=1e-12)
+
+
+def test_fp32_interpreter_predicts_device_tolerance():
+    """The device computes in fp32: emulate that rounding on the CPU and check it stays
+    inside the 1e-6 relative budget on the benchmark grid (100 nodes, 70 eliminations)."""
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    codes = wl.codes(bn, 12, seed=9)
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    got64 = program_interp.run(plan.words, plan.table_blob64, codes)
+    got32 = program_interp.run(plan.words, plan.table_blob, codes, dtype=np.float32)
+    assert np.max(np.abs(got32 - got64) / got64) < 1e-6
+    assert np.isfinite(got32).all()
+    # and the float64 program equals the oracle run with the same elimination order
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    order = [net.names[v] for v in plan.order]
+    for b in range(3):
+        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        assert np.allclose(got64[:, b], want, rtol=1e-10)
+
+
+def test_benchmark_grid_plan_shape():
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    assert len(plan.order) == 100 - 1 - 30  # every node is an ancestor of the corner
+    assert plan.Q == 5
+    assert plan.max_factor_per_row() <= 5 ** 6
+    assert plan.bytes_per_row() > 10_000  # a real streaming workload, not a toy
+    # slot reuse keeps the per-row scratch far below the sum of all intermediates
+    total = sum(int(np.prod(st.cards)) for st in plan.steps)
+    assert plan.scratch_floats_per_row() < total
+
+
+def test_many_factors_are_folded_in_chunks():
+    """A root with 12 hidden children: eliminating it multiplies 13 factors, more than
+    one launch fuses (MAX_IN = 8) -> product-only launches first (bayes_net.py:256
+    reduces pairwise; the result is the same)."""
+    kids = [f"k{i:02d}" for i in range(12)]
+    bn = BayesNet(*[("root", k) for k in kids])
+    rng = np.random.default_rng(0)
+    import pandas as pd
+
+    bn.P["root"] = pd.Series({0: 0.3, 1: 0.7})
+    for k in kids:
+        p = rng.random(2)
+        bn.P[k] = pd.DataFrame({"root": [0, 0, 1, 1], k: [0, 1, 0, 1], "p": [p[0], 1 - p[0], p[1], 1 - p[1]]})
+    bn.prepare()
+    query, evs = kids[:2], kids[2:5]
+    codes = np.array([[0, 1, 1], [1, 0, 1], [0, 0, 1]], dtype=np.uint8)
+    # make every child *hidden-free*: query two, observe three, the other seven are hidden
+    plan, got = run_plan(bn, query, evs, codes, planner.MODE_BATCHED)
+    want = oracle_rows(bn, query, evs, codes)
+    assert np.allclose(got, want, rtol=1e-12)
+    assert max(len(st.inputs) for st in plan.steps) <= planner.MAX_IN
+    plan4, got4 = run_plan(bn, query, evs, codes, planner.MODE_BATCHED, max_in=2)
+    assert np.allclose(got4, want, rtol=1e-12)
+    assert max(len(st.inputs) for st in plan4.steps) <= 2 and len(plan4.steps) > len(plan.steps)
+
+
+def test_custom_elimination_order_and_errors():
+    bn = examples.asia()
+    net = bn._compiled
+    q = [net.index["Dispnea"]]
+    e = [net.index["Visit to Asia"]]
+    hidden = [net.index[n] for n in ("Tuberculosis", "Smoker", "Lung cancer", "Bronchitis", "TB or cancer")]
+    codes = np.array([[1]], dtype=np.uint8)
+    base = None
+    for order in (hidden, hidden[::-1]):
+        plan = planner.build_plan(net, q, e, mode=planner.MODE_FLAT, order=order)
+        got = program_interp.run(plan.words, plan.table_blob64, codes)
+        base = got if base is None else base
+        assert np.allclose(got, base, rtol=1e-13)
+    with pytest.raises(ValueError):
+        planner.build_plan(net, q, e, order=hidden[:-1])
+    with pytest.raises(ValueError):  # bayes_net.py:840-841
+        planner.build_plan(net, [], e)
+    with pytest.raises(ValueError):  # bayes_net.py:843-845
+        planner.build_plan(net, q, q)
+
+
+def test_program_words_are_self_consistent():
+    bn = examples.alarm()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index["Burglary"]], [net.index["John calls"], net.index["Mary calls"]])
+    hdr, tables, slots, steps = program_interp.parse(plan.words)
+    assert hdr["version"] == planner.VERSION and hdr["n_ev"] == 2 and hdr["Q"] == 2
+    assert all(off % 4 == 0 for off, _ in tables)  # 16-byte aligned tables (bulk-TMA copies)
+    assert steps[-1]["out_slot"] == hdr["post_slot"]
+    assert plan.words.dtype == np.int32 and plan.table_blob.dtype == np.float32
+    # evidence axes carry (column, stride, cardinality)
+    evs = [e for st in steps for i in st["inputs"] for e in i["ev"]]
+    assert evs and all(0 <= col < 2 and card == 2 for col, _, card in evs)
+
+
+def test_tables_are_shipped_as_plain_probabilities():
+    """No rescaling: with entries <= 1 every intermediate factor stays <= 1 in fp32."""
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    assert set(plan.table_scale_log2) == {0}
+    assert plan.table_blob.max() <= 1.0 and plan.table_blob.min() >= 0.0
