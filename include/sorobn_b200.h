@@ -96,8 +96,9 @@ int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 /* Toggle CUDA-graph replay of the step sequence (default on). */
 int sbn_program_set_graph(sbn_program *prog, int enabled);
 
-/* Toggle the register-tiled step kernel (default on; off = the plain one-output-per-
- * iteration kernel, kept as the general fallback and as a cross-check in tests). */
+/* Select the step kernel: 0 = the plain one-output-per-iteration kernel (general
+ * fallback, cross-check in tests); 1 = register-tiled kernel (default); 2 or 4 = tiled
+ * with that many evidence rows per thread. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* Pinned host memory for evidence / posterior staging buffers. */

@@ -295,8 +295,12 @@ class BayesNet:
         if algorithm != "exact":
             raise NotImplementedError("query_many only implements algorithm='exact'")
         plan, program = self._plan(query, ev_vars, _planner.MODE_BATCHED)
+        n = len(events.index)
+        if n == 0:
+            return pd.DataFrame(np.zeros((0, plan.Q)), index=events.index, columns=self._answer_index(plan))
         codes, bad = self._encode_events(ev_vars, [events[v].to_numpy() for v in ev_vars])
-        n = len(events)
+        if not ev_vars:
+            bad = np.zeros(n, dtype=bool)
         post = program.run(codes, n)  # [Q, n]
         out = pd.DataFrame(post.T.astype(np.float64), index=events.index, columns=self._answer_index(plan))
         if bad.any():

@@ -62,6 +62,8 @@ struct StepDesc {
     std::vector<InDesc> in;
     // tiled fast path (sbn_step_tiled): tile edge, tile count, offset-table position
     int tile = 0;            // 0 = not eligible, use sbn_step_batched
+    int nu = 0, na = 0, nb = 0;  // inputs without a tile axis / with axis 0 / with axis 1
+    std::vector<int> order;      // kernel input slot -> index into `in` (U, then A, then B)
     int64_t n_tiles = 0;
     int64_t tile_off_pos = 0;  // int32 offset into sbn_program::d_tile_off
 };
@@ -96,6 +98,7 @@ struct sbn_program {
 
     bool use_graph = true;
     bool use_tiled = true;
+    int tiled_v = 2;  // evidence rows per thread of the tiled kernel (2 or 4)
     cudaGraphExec_t exec = nullptr;
     struct {
         const uint8_t *ev;
@@ -226,7 +229,6 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
     return SBN_OK;
 }
 
-constexpr int kTiledV = 2;             // evidence rows per thread of the tiled kernel
 constexpr int kTiledMaxIn = 4;
 constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 
@@ -245,6 +247,33 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         const int c0 = n_axes > 0 ? st.cards[0] : 1;
         const int c1 = n_axes > 1 ? st.cards[1] : 1;
         if (c0 > 255 * 5 || c1 > 255 * 5) continue;
+        // sort the inputs by the tile axes they carry
+        std::vector<int> us, as, bs;
+        bool both = false;
+        for (size_t i = 0; i < st.in.size(); ++i) {
+            const bool h0 = n_axes > 0 && st.in[i].strides[0] != 0;
+            const bool h1 = n_axes > 1 && st.in[i].strides[1] != 0;
+            if (h0 && h1) both = true;
+            else if (h0) as.push_back(static_cast<int>(i));
+            else if (h1) bs.push_back(static_cast<int>(i));
+            else us.push_back(static_cast<int>(i));
+        }
+        if (both) continue;  // an input spans the whole tile: sbn_step_batched streams it
+        // a factor without tile axes may ride on either side (stride 0 re-reads one entry)
+        while (us.size() > 2 || (as.empty() && !us.empty())) {
+            if (as.size() < 2) as.push_back(us.back());
+            else if (n_axes > 1 && bs.size() < 2) bs.push_back(us.back());
+            else break;
+            us.pop_back();
+        }
+        if (us.size() > 2 || as.empty() || as.size() > 2 || bs.size() > 2) continue;
+        if (n_axes > 1 && bs.empty()) continue;
+        st.nu = static_cast<int>(us.size());
+        st.na = static_cast<int>(as.size());
+        st.nb = static_cast<int>(bs.size());
+        st.order = us;
+        st.order.insert(st.order.end(), as.begin(), as.end());
+        st.order.insert(st.order.end(), bs.begin(), bs.end());
         // tile edge: least padding waste, ties to the larger tile
         int best_t = 2;
         double best_w = 1e30;
@@ -272,7 +301,7 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
             for (int j = 2; j < n_axes; ++j) {
                 const int d = static_cast<int>(q % st.cards[j]);
                 q /= st.cards[j];
-                for (int i = 0; i < n_in; ++i) off[i] += static_cast<int64_t>(d) * st.in[i].strides[j];
+                for (int i = 0; i < n_in; ++i) off[i] += static_cast<int64_t>(d) * st.in[st.order[i]].strides[j];
             }
             for (int tb = 0; tb < n_tb; ++tb) {
                 for (int ta = 0; ta < n_ta; ++ta) {
@@ -281,8 +310,8 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
                     words->push_back(na | (nb << 8));
                     for (int i = 0; i < n_in; ++i) {
                         int64_t o = off[i];
-                        if (n_axes > 0) o += static_cast<int64_t>(ta) * T * st.in[i].strides[0];
-                        if (n_axes > 1) o += static_cast<int64_t>(tb) * T * st.in[i].strides[1];
+                        if (n_axes > 0) o += static_cast<int64_t>(ta) * T * st.in[st.order[i]].strides[0];
+                        if (n_axes > 1) o += static_cast<int64_t>(tb) * T * st.in[st.order[i]].strides[1];
                         words->push_back(static_cast<int32_t>(o));
                     }
                 }
@@ -328,8 +357,9 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     q->n_out = static_cast<int32_t>(st.n_out);
     for (size_t j = 0; j < st.cards.size(); ++j) q->card[j] = st.cards[j];
     int smem = 0;
+    const bool tiled = st.kind == 1 && st.tile > 0 && P->use_tiled;
     for (size_t i = 0; i < st.in.size(); ++i) {
-        const InDesc &in = st.in[i];
+        const InDesc &in = st.in[tiled ? st.order[i] : i];
         SbnInput &d = q->in[i];
         int64_t padded;
         if (in.is_slot) {
@@ -359,8 +389,9 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         }
     }
     q->smem_floats = smem;
-    if (st.kind == 1 && st.tile > 0 && P->use_tiled) {
-        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * kTiledV;
+    q->n_cls3 = 0;
+    if (tiled) {
+        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * P->tiled_v;
         const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
         // enough CTAs for ~4 waves (148 SMs x ~6 resident CTAs), otherwise as many
         // consecutive tiles per CTA as possible (neighbouring tiles share operands in L1)
@@ -436,26 +467,53 @@ cudaError_t set_smem_attr_n() {
     return e;
 }
 
-template <int N_IN>
-cudaError_t launch_tiled_n(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
+// (NU, NA, NB) combinations instantiated: NU <= 2, 1 <= NA <= 2, NB <= 2, at most 4 inputs
+#define SBN_TILED_COMBOS(X) \
+    X(0, 1, 0) X(0, 1, 1) X(0, 1, 2) X(0, 2, 0) X(0, 2, 1) X(0, 2, 2) X(1, 1, 0) X(1, 1, 1) X(1, 1, 2) \
+    X(1, 2, 0) X(1, 2, 1) X(2, 1, 0) X(2, 1, 1) X(2, 2, 0)
+
+template <int NU, int NA, int NB, int V>
+cudaError_t launch_tiled_v(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
     const dim3 g(static_cast<unsigned>(grid)), b(SBN_TILED_THREADS);
     switch (tile) {
-        case 2: sbn_step_tiled<N_IN, 2, kTiledV><<<g, b, smem, stream>>>(q); break;
-        case 3: sbn_step_tiled<N_IN, 3, kTiledV><<<g, b, smem, stream>>>(q); break;
-        case 4: sbn_step_tiled<N_IN, 4, kTiledV><<<g, b, smem, stream>>>(q); break;
-        case 5: sbn_step_tiled<N_IN, 5, kTiledV><<<g, b, smem, stream>>>(q); break;
+        case 2: sbn_step_tiled<NU, NA, NB, 2, V><<<g, b, smem, stream>>>(q); break;
+        case 3: sbn_step_tiled<NU, NA, NB, 3, V><<<g, b, smem, stream>>>(q); break;
+        case 4: sbn_step_tiled<NU, NA, NB, 4, V><<<g, b, smem, stream>>>(q); break;
+        case 5: sbn_step_tiled<NU, NA, NB, 5, V><<<g, b, smem, stream>>>(q); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-template <int N_IN>
-cudaError_t set_tiled_attr_n() {
-    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 2, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 3, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 4, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<N_IN, 5, kTiledV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, int v, int64_t grid, cudaStream_t stream) {
+    const int key = st.nu * 100 + st.na * 10 + st.nb;
+    switch (key) {
+#define X(U, A, B)                                                                              \
+    case U * 100 + A * 10 + B:                                                                  \
+        return v == 4 ? launch_tiled_v<U, A, B, 4>(q, st.tile, grid, stream)                    \
+                      : launch_tiled_v<U, A, B, 2>(q, st.tile, grid, stream);
+        SBN_TILED_COMBOS(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NU, int NA, int NB, int V>
+cudaError_t set_tiled_attr_v() {
+    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 2, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 3, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 4, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 5, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    return e;
+}
+cudaError_t set_tiled_attrs() {
+    cudaError_t e = cudaSuccess;
+#define X(U, A, B)                                              \
+    if (e == cudaSuccess) e = set_tiled_attr_v<U, A, B, 2>();   \
+    if (e == cudaSuccess) e = set_tiled_attr_v<U, A, B, 4>();
+    SBN_TILED_COMBOS(X)
+#undef X
     return e;
 }
 
@@ -465,13 +523,7 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
         const int64_t chunks = (q.n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
         const int64_t grid = chunks * q.n_bblocks;
         if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
-        switch (q.n_in) {
-            case 1: return launch_tiled_n<1>(q, st.tile, grid, stream);
-            case 2: return launch_tiled_n<2>(q, st.tile, grid, stream);
-            case 3: return launch_tiled_n<3>(q, st.tile, grid, stream);
-            case 4: return launch_tiled_n<4>(q, st.tile, grid, stream);
-        }
-        return cudaErrorInvalidValue;
+        return launch_tiled(st, q, P->tiled_v, grid, stream);
     }
     if (st.kind == 0) {
         const int threads = 256;
@@ -632,10 +684,7 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
             SBN_CUDA_P(set_smem_attr_n<6>());
             SBN_CUDA_P(set_smem_attr_n<7>());
             SBN_CUDA_P(set_smem_attr_n<8>());
-            SBN_CUDA_P(set_tiled_attr_n<1>());
-            SBN_CUDA_P(set_tiled_attr_n<2>());
-            SBN_CUDA_P(set_tiled_attr_n<3>());
-            SBN_CUDA_P(set_tiled_attr_n<4>());
+            SBN_CUDA_P(set_tiled_attrs());
             done[device] = true;
         }
     }
@@ -817,11 +866,12 @@ int sbn_program_set_graph(sbn_program *P, int enabled) {
 
 int sbn_program_set_tiled(sbn_program *P, int enabled) {
     if (!P) return fail(SBN_E_INVALID, "null program");
-    if (P->use_tiled != (enabled != 0) && P->exec) {
+    if (P->exec) {
         cudaGraphExecDestroy(P->exec);
         P->exec = nullptr;
     }
     P->use_tiled = enabled != 0;
+    if (enabled == 4 || enabled == 2) P->tiled_v = enabled;
     return SBN_OK;
 }
 

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/sorobn_b200.h"
 
 #define SBN_THREADS 128      // threads per CTA of the batched kernel (4 rows each)
@@ -57,7 +59,7 @@ struct SbnStep {
     int32_t tiles_per_cta;            // tiled kernel: consecutive tiles one CTA walks
     const int32_t *tile_off;          // tiled kernel: [n_tiles][n_in + 2] = out entry, na | nb << 8, input offsets
     int32_t n_tiles;
-    int32_t pad_;
+    int32_t n_cls3;                   // tiled kernel: inputs that carry both tile axes
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -270,8 +272,16 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 
 #define SBN_TILED_THREADS 128
 
-template <int N_IN, int T, int V>
-__global__ void __launch_bounds__(SBN_TILED_THREADS, 4) sbn_step_tiled(const __grid_constant__ SbnStep p) {
+// Inputs arrive sorted by the host: NU that carry neither tile axis, then NA that carry
+// axis 0 only, then NB that carry axis 1 only (an input with both axes sends the step to
+// sbn_step_batched instead).  Per eliminated state x:
+//     a[d0] = prod_U in(x) * prod_A in(x, d0)      T values
+//     b[d1] = prod_B in(x, d1)                     T values
+//     acc[d0][d1] += a[d0] * b[d1]                 T*T FFMA
+template <int NU, int NA, int NB, int T, int V>
+__global__ void __launch_bounds__(SBN_TILED_THREADS, (V == 2 ? 4 : 2)) sbn_step_tiled(const __grid_constant__ SbnStep p) {
+    constexpr int N_IN = NU + NA + NB;
+    constexpr int TB = NB > 0 ? T : 1;  // no B-side input: the output has a single axis
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -299,12 +309,13 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, 4) sbn_step_tiled(const __g
     const int b = (rblock * SBN_TILED_THREADS + threadIdx.x) * V;
     const bool live = b < p.n_rows;  // b % V == 0 and ld % 32 == 0: the vector stays inside the pitch
 
-    // per-row evidence offsets of the gathered tables
-    int evo[N_IN][V];
+    const float *gsrc[N_IN];  // global, row b (batched inputs)
+    int evo[N_IN][V];         // shared-memory float offset of the table copy + this row's evidence offset
 #pragma unroll
     for (int i = 0; i < N_IN; ++i) {
+        gsrc[i] = p.in[i].ptr + b;
 #pragma unroll
-        for (int l = 0; l < V; ++l) evo[i][l] = 0;
+        for (int l = 0; l < V; ++l) evo[i][l] = p.in[i].smem_off;
         if (!p.in[i].batched && live) {
             for (int k = 0; k < p.in[i].n_ev; ++k) {
                 const uint8_t *col = p.ev + static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev + b;
@@ -322,21 +333,11 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, 4) sbn_step_tiled(const __g
     if (staged) sbn_mbar_wait(&s_bar, 0);
     if (!live) return;
 
-    const int64_t ld = p.ld;
+    const int ld = static_cast<int>(p.ld);
     const int c0 = p.n_axes > 0 ? p.card[0] : 1;
     const int t_begin = chunk * p.tiles_per_cta;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
-
-    // one value (V rows) of input i at element offset e
-    auto fetch = [&](int i, int e, float (&r)[V]) {
-        if (p.in[i].batched) {
-            sbn_ldv<V>(r, p.in[i].ptr + static_cast<int64_t>(e) * ld + b);
-        } else {
-            const float *t = s_tab + p.in[i].smem_off + e;
-#pragma unroll
-            for (int l = 0; l < V; ++l) r[l] = t[evo[i][l]];
-        }
-    };
+    float *const outp = p.out + b;
 
     for (int t = t_begin; t < t_end; ++t) {
         const int32_t *row = p.tile_off + static_cast<int64_t>(t) * (N_IN + 2);
@@ -347,87 +348,108 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, 4) sbn_step_tiled(const __g
 #pragma unroll
         for (int i = 0; i < N_IN; ++i) base[i] = __ldg(row + 2 + i);
 
-        float acc[T][T][V];
+        float acc[T][TB][V];
 #pragma unroll
         for (int d0 = 0; d0 < T; ++d0)
 #pragma unroll
-            for (int d1 = 0; d1 < T; ++d1)
+            for (int d1 = 0; d1 < TB; ++d1)
 #pragma unroll
                 for (int l = 0; l < V; ++l) acc[d0][d1][l] = 0.f;
 
-        for (int x = 0; x < p.cx; ++x) {
-            float u[V], a[T][V], bb[T][V];
+        // FULL = whole T x TB tile.  Otherwise digits past the edge re-read the last valid
+        // entry (clamped, so every load stays in bounds) and only the stores are predicated.
+        auto run_tile = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            int k0[T], k1[TB];  // element-offset multipliers of the tile digits
 #pragma unroll
-            for (int l = 0; l < V; ++l) u[l] = 1.f;
+            for (int d = 0; d < T; ++d) k0[d] = FULL ? d : min(d, na - 1);
 #pragma unroll
-            for (int d = 0; d < T; ++d)
-#pragma unroll
-                for (int l = 0; l < V; ++l) a[d][l] = bb[d][l] = 1.f;
+            for (int d = 0; d < TB; ++d) k1[d] = FULL ? d : min(d, nb - 1);
 
+#pragma unroll 2
+            for (int x = 0; x < p.cx; ++x) {
+                float a[T][V], bb[TB][V];
+                // ---- A side (first A input initialises, the others multiply in)
 #pragma unroll
-            for (int i = 0; i < N_IN; ++i) {
-                const int e = base[i] + x * p.in[i].sx;
-                const int cls = p.in[i].cls;
-                if (cls == 0) {
-                    float r[V];
-                    fetch(i, e, r);
-#pragma unroll
-                    for (int l = 0; l < V; ++l) u[l] *= r[l];
-                } else if (cls == 1) {
+                for (int j = 0; j < NA; ++j) {
+                    const int i = NU + j;
+                    const int e = base[i] + x * p.in[i].sx;
                     const int s0 = p.in[i].stride[0];
+                    float r[T][V];
+                    if (p.in[i].batched) {
 #pragma unroll
-                    for (int d0 = 0; d0 < T; ++d0) {
-                        if (d0 < na) {
-                            float r[V];
-                            fetch(i, e + d0 * s0, r);
+                        for (int d = 0; d < T; ++d) sbn_ldv<V>(r[d], gsrc[i] + static_cast<int64_t>(e + k0[d] * s0) * ld);
+                    } else {
 #pragma unroll
-                            for (int l = 0; l < V; ++l) a[d0][l] *= r[l];
-                        }
+                        for (int d = 0; d < T; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) r[d][l] = s_tab[evo[i][l] + e + k0[d] * s0];
                     }
-                } else if (cls == 2) {
+#pragma unroll
+                    for (int d = 0; d < T; ++d)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) a[d][l] = (j == 0) ? r[d][l] : a[d][l] * r[d][l];
+                }
+                // ---- U side folds into a[]
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                    const int e = base[i] + x * p.in[i].sx;
+                    float r[V];
+                    if (p.in[i].batched) {
+                        sbn_ldv<V>(r, gsrc[i] + static_cast<int64_t>(e) * ld);
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < V; ++l) r[l] = s_tab[evo[i][l] + e];
+                    }
+#pragma unroll
+                    for (int d = 0; d < T; ++d)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) a[d][l] *= r[l];
+                }
+                // ---- B side
+                if constexpr (NB == 0) {
+#pragma unroll
+                    for (int l = 0; l < V; ++l) bb[0][l] = 1.f;
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int i = NU + NA + j;
+                    const int e = base[i] + x * p.in[i].sx;
                     const int s1 = p.in[i].stride[1];
+                    float r[TB][V];
+                    if (p.in[i].batched) {
 #pragma unroll
-                    for (int d1 = 0; d1 < T; ++d1) {
-                        if (d1 < nb) {
-                            float r[V];
-                            fetch(i, e + d1 * s1, r);
+                        for (int d = 0; d < TB; ++d) sbn_ldv<V>(r[d], gsrc[i] + static_cast<int64_t>(e + k1[d] * s1) * ld);
+                    } else {
 #pragma unroll
-                            for (int l = 0; l < V; ++l) bb[d1][l] *= r[l];
-                        }
+                        for (int d = 0; d < TB; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) r[d][l] = s_tab[evo[i][l] + e + k1[d] * s1];
                     }
+#pragma unroll
+                    for (int d = 0; d < TB; ++d)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) bb[d][l] = (j == 0) ? r[d][l] : bb[d][l] * r[d][l];
                 }
+                // ---- outer product into the accumulators
+#pragma unroll
+                for (int d0 = 0; d0 < T; ++d0)
+#pragma unroll
+                    for (int d1 = 0; d1 < TB; ++d1)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
             }
 #pragma unroll
-            for (int d0 = 0; d0 < T; ++d0) {
+            for (int d1 = 0; d1 < TB; ++d1)
 #pragma unroll
-                for (int d1 = 0; d1 < T; ++d1) {
-                    if (d0 < na && d1 < nb) {
-                        float w[V];
-#pragma unroll
-                        for (int l = 0; l < V; ++l) w[l] = u[l] * a[d0][l] * bb[d1][l];
-#pragma unroll
-                        for (int i = 0; i < N_IN; ++i) {
-                            if (p.in[i].cls == 3) {
-                                float r[V];
-                                fetch(i, base[i] + x * p.in[i].sx + d0 * p.in[i].stride[0] + d1 * p.in[i].stride[1], r);
-#pragma unroll
-                                for (int l = 0; l < V; ++l) w[l] *= r[l];
-                            }
-                        }
-#pragma unroll
-                        for (int l = 0; l < V; ++l) acc[d0][d1][l] += w[l];
-                    }
-                }
-            }
-        }
-
-#pragma unroll
-        for (int d1 = 0; d1 < T; ++d1) {
-#pragma unroll
-            for (int d0 = 0; d0 < T; ++d0) {
-                if (d0 < na && d1 < nb)
-                    sbn_stv<V>(p.out + static_cast<int64_t>(o_base + d1 * c0 + d0) * ld + b, acc[d0][d1]);
-            }
+                for (int d0 = 0; d0 < T; ++d0)
+                    if (FULL || (d0 < na && d1 < nb))
+                        sbn_stv<V>(outp + static_cast<int64_t>(o_base + d1 * c0 + d0) * ld, acc[d0][d1]);
+        };
+        if (na == T && nb == TB) {
+            run_tile(std::true_type{});
+        } else {
+            run_tile(std::false_type{});
         }
     }
 }

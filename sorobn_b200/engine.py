@@ -137,6 +137,11 @@ class Program:
         blob = np.ascontiguousarray(plan.table_blob, dtype=np.float32)
         _check(lib.sbn_program_create(self.device, words.ctypes.data, words.size, blob.ctypes.data, blob.size,
                                       ctypes.byref(self._h)))
+        # developer switches (profiling / A-B runs); the defaults are the fast path
+        if os.environ.get("SOROBN_B200_TILED"):
+            self.set_tiled(int(os.environ["SOROBN_B200_TILED"]))
+        if os.environ.get("SOROBN_B200_GRAPH"):
+            self.set_graph(int(os.environ["SOROBN_B200_GRAPH"]))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -156,8 +161,9 @@ class Program:
     def set_graph(self, enabled: bool):
         _check(load().sbn_program_set_graph(self._h, int(bool(enabled))))
 
-    def set_tiled(self, enabled: bool):
-        _check(load().sbn_program_set_tiled(self._h, int(bool(enabled))))
+    def set_tiled(self, mode):
+        """False/0: plain kernel; True/1: tiled (default); 2 or 4: tiled with that many rows per thread."""
+        _check(load().sbn_program_set_tiled(self._h, int(mode)))
 
     def info(self) -> dict:
         buf = (ctypes.c_int64 * 8)()

@@ -58,7 +58,7 @@ def test_query_many_matches_reference_goldens(name):
         groups.setdefault(key, []).append(case)
     worst = 0.0
     for (query, ev_vars), cases in groups.items():
-        events = pd.DataFrame([case_event(c) for c in cases], columns=list(ev_vars))
+        events = pd.DataFrame([case_event(c) for c in cases], columns=list(ev_vars), index=range(len(cases)))
         got = bn.query_many(*query, events=events)
         assert got.shape[0] == len(cases)
         domains = {n: net.domains[net.index[n]] for n in cases[0]["names"]}
@@ -191,7 +191,10 @@ def test_random_networks_batched_vs_oracle():
         evs = [spec.nodes[i] for i in perm[nq:nq + ne]]
         B = 70
         events = synthetic.random_events(spec, evs, B, seed=trial)
+        if not evs:
+            events = pd.DataFrame(index=range(B))
         got = bn.query_many(*query, events=events).to_numpy()
+        assert got.shape[0] == B
         for b in range(0, B, 7):
             ev = {v: int(events[v].iloc[b]) for v in evs}
             want = ve_oracle.query(net, *query, event=ev)[1].reshape(-1)
