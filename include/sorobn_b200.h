@@ -97,8 +97,8 @@ int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 int sbn_program_set_graph(sbn_program *prog, int enabled);
 
 /* Select the step kernel: 0 = the plain one-output-per-iteration kernel (general
- * fallback, cross-check in tests); 1 = register-tiled kernel (default); 2 or 4 = tiled
- * with that many evidence rows per thread. */
+ * fallback, cross-check in tests); 1 or 2 = register-tiled kernel with the operand
+ * preload schedule where available (default); 4 = tiled, x-loop schedule only. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* Pinned host memory for evidence / posterior staging buffers. */

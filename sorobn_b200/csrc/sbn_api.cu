@@ -98,7 +98,7 @@ struct sbn_program {
 
     bool use_graph = true;
     bool use_tiled = true;
-    int tiled_v = 2;  // evidence rows per thread of the tiled kernel (2 or 4)
+    int tiled_v = 2;  // 2 = preload schedule where available (default), 4 = always the x-loop schedule
     cudaGraphExec_t exec = nullptr;
     struct {
         const uint8_t *ev;
@@ -230,6 +230,7 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
 }
 
 constexpr int kTiledMaxIn = 4;
+constexpr int kRowsPerThread = 2;
 constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 
 // Host half of the tiled kernel: pick the tile edge and precompute, for every tile, the
@@ -389,9 +390,8 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         }
     }
     q->smem_floats = smem;
-    q->n_cls3 = 0;
     if (tiled) {
-        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * P->tiled_v;
+        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * kRowsPerThread;
         const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
         // enough CTAs for ~4 waves (148 SMs x ~6 resident CTAs), otherwise as many
         // consecutive tiles per CTA as possible (neighbouring tiles share operands in L1)
@@ -400,6 +400,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
         q->tiles_per_cta = static_cast<int32_t>(tpc);
         q->n_tiles = static_cast<int32_t>(st.n_tiles);
+        q->n_chunks = static_cast<int32_t>((st.n_tiles + tpc - 1) / tpc);
         q->tile_off = P->d_tile_off + st.tile_off_pos;
         q->n_bblocks = static_cast<int32_t>(n_rblocks);
         q->tile1 = 0;
@@ -472,46 +473,60 @@ cudaError_t set_smem_attr_n() {
     X(0, 1, 0) X(0, 1, 1) X(0, 1, 2) X(0, 2, 0) X(0, 2, 1) X(0, 2, 2) X(1, 1, 0) X(1, 1, 1) X(1, 1, 2) \
     X(1, 2, 0) X(1, 2, 1) X(2, 1, 0) X(2, 1, 1) X(2, 2, 0)
 
-template <int NU, int NA, int NB, int V>
-cudaError_t launch_tiled_v(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
+constexpr int kV = kRowsPerThread;  // evidence rows per thread of the tiled kernel
+
+// Preload variants (CX > 0) exist where the tile edge equals the eliminated cardinality
+// (networks with one cardinality throughout: 2, 3, 4, 5 states) and for 8 states (T = 4).
+template <int NU, int NA, int NB>
+cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t grid, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
     const dim3 g(static_cast<unsigned>(grid)), b(SBN_TILED_THREADS);
+#define SBN_T(TV)                                                                      \
+    case TV:                                                                           \
+        if (preload && q.cx == TV) sbn_step_tiled<NU, NA, NB, TV, kV, TV><<<g, b, smem, stream>>>(q); \
+        else sbn_step_tiled<NU, NA, NB, TV, kV, 0><<<g, b, smem, stream>>>(q);         \
+        break;
     switch (tile) {
-        case 2: sbn_step_tiled<NU, NA, NB, 2, V><<<g, b, smem, stream>>>(q); break;
-        case 3: sbn_step_tiled<NU, NA, NB, 3, V><<<g, b, smem, stream>>>(q); break;
-        case 4: sbn_step_tiled<NU, NA, NB, 4, V><<<g, b, smem, stream>>>(q); break;
-        case 5: sbn_step_tiled<NU, NA, NB, 5, V><<<g, b, smem, stream>>>(q); break;
+        SBN_T(2)
+        SBN_T(3)
+        SBN_T(5)
+        case 4:
+            if (preload && q.cx == 4) sbn_step_tiled<NU, NA, NB, 4, kV, 4><<<g, b, smem, stream>>>(q);
+            else if (preload && q.cx == 8) sbn_step_tiled<NU, NA, NB, 4, kV, 8><<<g, b, smem, stream>>>(q);
+            else sbn_step_tiled<NU, NA, NB, 4, kV, 0><<<g, b, smem, stream>>>(q);
+            break;
         default: return cudaErrorInvalidValue;
     }
+#undef SBN_T
     return cudaGetLastError();
 }
 
-cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, int v, int64_t grid, cudaStream_t stream) {
+cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int64_t grid, cudaStream_t stream) {
     const int key = st.nu * 100 + st.na * 10 + st.nb;
+    // the preload schedule keeps every operand of a tile in registers: only for <= 3 inputs
+    preload = preload && st.in.size() <= 3;
     switch (key) {
-#define X(U, A, B)                                                                              \
-    case U * 100 + A * 10 + B:                                                                  \
-        return v == 4 ? launch_tiled_v<U, A, B, 4>(q, st.tile, grid, stream)                    \
-                      : launch_tiled_v<U, A, B, 2>(q, st.tile, grid, stream);
+#define X(U, A, B) \
+    case U * 100 + A * 10 + B: return launch_tiled_c<U, A, B>(q, st.tile, preload, grid, stream);
         SBN_TILED_COMBOS(X)
 #undef X
     }
     return cudaErrorInvalidValue;
 }
 
-template <int NU, int NA, int NB, int V>
-cudaError_t set_tiled_attr_v() {
-    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 2, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 3, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 4, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, 5, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+template <int NU, int NA, int NB>
+cudaError_t set_tiled_attr_c() {
+    cudaError_t e = cudaSuccess;
+#define SBN_A(TV, CXV) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    SBN_A(2, 0) SBN_A(2, 2) SBN_A(3, 0) SBN_A(3, 3) SBN_A(4, 0) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 0) SBN_A(5, 5)
+#undef SBN_A
     return e;
 }
 cudaError_t set_tiled_attrs() {
     cudaError_t e = cudaSuccess;
-#define X(U, A, B)                                              \
-    if (e == cudaSuccess) e = set_tiled_attr_v<U, A, B, 2>();   \
-    if (e == cudaSuccess) e = set_tiled_attr_v<U, A, B, 4>();
+#define X(U, A, B) \
+    if (e == cudaSuccess) e = set_tiled_attr_c<U, A, B>();
     SBN_TILED_COMBOS(X)
 #undef X
     return e;
@@ -523,7 +538,7 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
         const int64_t chunks = (q.n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
         const int64_t grid = chunks * q.n_bblocks;
         if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
-        return launch_tiled(st, q, P->tiled_v, grid, stream);
+        return launch_tiled(st, q, P->tiled_v == 2, grid, stream);
     }
     if (st.kind == 0) {
         const int threads = 256;

@@ -59,7 +59,7 @@ struct SbnStep {
     int32_t tiles_per_cta;            // tiled kernel: consecutive tiles one CTA walks
     const int32_t *tile_off;          // tiled kernel: [n_tiles][n_in + 2] = out entry, na | nb << 8, input offsets
     int32_t n_tiles;
-    int32_t n_cls3;                   // tiled kernel: inputs that carry both tile axes
+    int32_t n_chunks;                 // tiled kernel: ceil(n_tiles / tiles_per_cta)
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -278,8 +278,13 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 //     a[d0] = prod_U in(x) * prod_A in(x, d0)      T values
 //     b[d1] = prod_B in(x, d1)                     T values
 //     acc[d0][d1] += a[d0] * b[d1]                 T*T FFMA
-template <int NU, int NA, int NB, int T, int V>
-__global__ void __launch_bounds__(SBN_TILED_THREADS, (V == 2 ? 4 : 2)) sbn_step_tiled(const __grid_constant__ SbnStep p) {
+//
+// CX > 0 (compile-time number of eliminated states) selects the *preload* schedule: every
+// operand of the tile, for all x, is fetched into registers before the first FFMA, so a
+// thread keeps CX * (NA * T + NB * T + NU) loads in flight instead of one x-step's worth
+// (the kernel is latency-bound otherwise: ~16 warps per SM because of the accumulators).
+template <int NU, int NA, int NB, int T, int V, int CX>
+__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_tiled(const __grid_constant__ SbnStep p) {
     constexpr int N_IN = NU + NA + NB;
     constexpr int TB = NB > 0 ? T : 1;  // no B-side input: the output has a single axis
     extern __shared__ __align__(16) float s_tab[];
@@ -304,8 +309,10 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (V == 2 ? 4 : 2)) sbn_step_
         }
     }
 
-    const int rblock = blockIdx.x % p.n_bblocks;
-    const int chunk = blockIdx.x / p.n_bblocks;
+    // Tile chunks vary fastest: the CTAs resident at any moment then cover all tiles of a
+    // few row blocks, so operands shared between tiles are re-read from L2, not from HBM.
+    const int rblock = blockIdx.x / p.n_chunks;
+    const int chunk = blockIdx.x % p.n_chunks;
     const int b = (rblock * SBN_TILED_THREADS + threadIdx.x) * V;
     const bool live = b < p.n_rows;  // b % V == 0 and ld % 32 == 0: the vector stays inside the pitch
 
@@ -366,6 +373,95 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (V == 2 ? 4 : 2)) sbn_step_
 #pragma unroll
             for (int d = 0; d < TB; ++d) k1[d] = FULL ? d : min(d, nb - 1);
 
+            if constexpr (CX > 0) {
+                // ---- preload schedule: all loads first ...
+                float ra[NA][CX][T][V], rb[NB > 0 ? NB : 1][CX][TB][V], ru[NU > 0 ? NU : 1][CX][V];
+#pragma unroll
+                for (int j = 0; j < NA; ++j) {
+                    const int i = NU + j;
+                    const int s0 = p.in[i].stride[0], sx = p.in[i].sx;
+                    if (p.in[i].batched) {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < T; ++d)
+                                sbn_ldv<V>(ra[j][x][d], gsrc[i] + static_cast<int64_t>(base[i] + x * sx + k0[d] * s0) * ld);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < T; ++d)
+#pragma unroll
+                                for (int l = 0; l < V; ++l) ra[j][x][d][l] = s_tab[evo[i][l] + base[i] + x * sx + k0[d] * s0];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int i = NU + NA + j;
+                    const int s1 = p.in[i].stride[1], sx = p.in[i].sx;
+                    if (p.in[i].batched) {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < TB; ++d)
+                                sbn_ldv<V>(rb[j][x][d], gsrc[i] + static_cast<int64_t>(base[i] + x * sx + k1[d] * s1) * ld);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < TB; ++d)
+#pragma unroll
+                                for (int l = 0; l < V; ++l) rb[j][x][d][l] = s_tab[evo[i][l] + base[i] + x * sx + k1[d] * s1];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                    const int sx = p.in[i].sx;
+                    if (p.in[i].batched) {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x) sbn_ldv<V>(ru[i][x], gsrc[i] + static_cast<int64_t>(base[i] + x * sx) * ld);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) ru[i][x][l] = s_tab[evo[i][l] + base[i] + x * sx];
+                    }
+                }
+                // ---- ... then the arithmetic
+#pragma unroll
+                for (int x = 0; x < CX; ++x) {
+                    float a[T][V], bb[TB][V];
+#pragma unroll
+                    for (int d = 0; d < T; ++d)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) {
+                            float v = ra[0][x][d][l];
+#pragma unroll
+                            for (int j = 1; j < NA; ++j) v *= ra[j][x][d][l];
+#pragma unroll
+                            for (int i = 0; i < NU; ++i) v *= ru[i][x][l];
+                            a[d][l] = v;
+                        }
+#pragma unroll
+                    for (int d = 0; d < TB; ++d)
+#pragma unroll
+                        for (int l = 0; l < V; ++l) {
+                            float v = 1.f;
+                            if constexpr (NB > 0) {
+                                v = rb[0][x][d][l];
+#pragma unroll
+                                for (int j = 1; j < NB; ++j) v *= rb[j][x][d][l];
+                            }
+                            bb[d][l] = v;
+                        }
+#pragma unroll
+                    for (int d0 = 0; d0 < T; ++d0)
+#pragma unroll
+                        for (int d1 = 0; d1 < TB; ++d1)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                }
+            } else {
 #pragma unroll 2
             for (int x = 0; x < p.cx; ++x) {
                 float a[T][V], bb[TB][V];
@@ -438,6 +534,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (V == 2 ? 4 : 2)) sbn_step_
                     for (int d1 = 0; d1 < TB; ++d1)
 #pragma unroll
                         for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+            }
             }
 #pragma unroll
             for (int d1 = 0; d1 < TB; ++d1)
