@@ -170,7 +170,7 @@ def run_reference(args, rank, world):
     wl = workloads.WORKLOADS[args.workload]()
     bn = wl.build()
     cores = os.cpu_count() or 1
-    sample = args.cpu_rows or {"grid10x10": 64 * cores, "asia_1m": 2000 * cores, "dag50": 64 * cores}.get(args.workload, 64 * cores)
+    sample = args.cpu_rows or {"grid10x10": 512 * cores, "asia_1m": 20000 * cores, "dag50": 256 * cores}.get(args.workload, 256 * cores)
     codes = wl.codes(bn, sample, seed=0)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_rate(args.workload, codes, max(cores, sample // 8), cores)
@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
 
         cpu = None
         if not args.no_cpu_baseline:
-            n_cpu = args.cpu_rows or {"grid10x10": 2048, "asia_1m": 20000, "dag50": 1024}.get(wl.name, 1024)
+            n_cpu = args.cpu_rows or {"grid10x10": 8192, "asia_1m": 100000, "dag50": 4096}.get(wl.name, 4096)
             codes_cpu = np.ascontiguousarray(codes_host.array[:n_ev, :n_cpu])
             rate = cpu_rate(wl.name, codes_cpu, n_cpu, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
