@@ -56,27 +56,34 @@ def parse_args():
 
 # ------------------------------------------------------------------ clocks sampling
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML every ~2 ms while the
+    timed region runs (the CLI nvidia-smi is too slow for a 50 ms region)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.reasons_seen = [], 0
+        self.max_sm = None
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._ok = False
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self._stop.wait(0.002)
+        except Exception:
+            self._ok = False
 
     def __enter__(self):
         self._thread.start()
@@ -87,14 +94,13 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self._ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = [n for n, b in bits.items() if self.reasons_seen & b]
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.sm)}
 
 
 # --------------------------------------------------------------------- CPU baseline
@@ -129,6 +135,9 @@ def cpu_rate(workload: str, codes: np.ndarray, n_rows: int, n_procs: int):
         return n_rows / (time.perf_counter() - t0)
     bounds = np.linspace(0, n_rows, n_procs + 1).astype(int)
     jobs = [(workload, codes, int(bounds[i]), int(bounds[i + 1])) for i in range(n_procs) if bounds[i + 1] > bounds[i]]
+    # one single-threaded worker per core: numpy's own thread pools would oversubscribe
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
     ctx = mp.get_context("spawn")
     with ctx.Pool(len(jobs)) as pool:
         pool.map(_cpu_worker, [(workload, codes, 0, 1)] * len(jobs))  # warm: imports + network build
@@ -300,12 +309,13 @@ def run_b200(args, rank, world, local_rank):
         peak, peak_src = measured_peak()
         achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
         roofline = {
-            "bound": "hbm", "kernel": "sbn_step_batched", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "sbn_step_tiled (+ sbn_step_batched on sum-out-only steps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": peak_src,
             "algorithmic_bytes_per_step": kernel_bytes, "kernel_ms_per_step": kernel_ms,
             "launches_per_step": int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED)),
             "whole_step_frac": (plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9) / peak,
-            "traffic": ncu_traffic(wl.name),
+            "traffic": (ncu_traffic(wl.name) or {}).get("dram_bytes_per_step") if rows == wl.default_rows else None,
+            "traffic_detail": ncu_traffic(wl.name) if rows == wl.default_rows else None,
         }
         if args.dump:
             with open(args.dump, "w") as f:

@@ -60,7 +60,12 @@ traffic = {}
 if os.path.exists(traffic_path):
     traffic = json.load(open(traffic_path))
 dom = max(by_kernel.items(), key=lambda kv: kv[1]["us"])
-traffic[workload] = {"kernel": dom[0], "dram_bytes_per_step": dom[1]["dram_bytes"], "launches_per_step": dom[1]["launches"],
-                     "dram_bytes_per_launch": dom[1]["dram_bytes"] / dom[1]["launches"], "source": os.path.basename(prefix) + f"_launches_{workload}.csv"}
+steps_only = {k: v for k, v in by_kernel.items() if k.startswith("sbn_step")}
+traffic[workload] = {
+    "dram_bytes_per_step": sum(v["dram_bytes"] for v in steps_only.values()),
+    "launches_per_step": sum(v["launches"] for v in steps_only.values()),
+    "dominant_kernel": dom[0], "dominant_dram_bytes_per_step": dom[1]["dram_bytes"],
+    "dominant_launches_per_step": dom[1]["launches"],
+    "source": "profiles/" + os.path.basename(prefix) + f"_launches_{workload}.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 print(json.dumps(summary, indent=1))
