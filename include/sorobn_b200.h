@@ -27,7 +27,8 @@
  * name and the last one varying fastest -- the row order of the reference's answer
  * (`reorder_levels(sorted(...))`, `sort_index()`; bayes_net.py:872-875).
  * A row whose evidence has probability zero yields NaN (the reference returns an
- * empty Series there).
+ * empty Series there).  In float32 programs a row whose normaliser is below 1e-24 is also
+ * NaN: float32 underflow may have dropped addends; re-run it with a float64 program.
  *
  * Every function returns 0 on success or a negative SBN_E_* code;
  * sbn_last_error() then describes the failure (thread-local string).
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 2
+#define SBN_ABI_VERSION 3
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -68,6 +69,13 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
                        int64_t n_table_floats, sbn_program **out);
 void sbn_program_destroy(sbn_program *prog);
 
+/* Same for a single-event ("flat", mode 0) program evaluated in float64: tables, scratch
+ * and the posterior are doubles.  One query is launch-latency bound, so it gets the
+ * reference's own precision and range (float64, bayes_net.py throughout) for free; it is
+ * also the fallback for evidence rows too unlikely for float32 (see run_host below). */
+int sbn_program_create_f64(int device, const int32_t *words, int64_t n_words, const double *tables,
+                           int64_t n_table_doubles, sbn_program **out);
+
 /* Allocate scratch for chunks of up to `max_rows` evidence rows (larger batches are
  * processed in chunks).  Called implicitly by the run functions when needed. */
 int sbn_program_reserve(sbn_program *prog, int64_t max_rows);
@@ -77,6 +85,10 @@ int sbn_program_reserve(sbn_program *prog, int64_t max_rows);
  * replaces `BayesNet._variable_elimination` (bayes_net.py:739) for a batch of events. */
 int sbn_program_run_host(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out,
                          int64_t ld_out);
+
+/* float64 programs (n_rows must be 1). */
+int sbn_program_run_host_f64(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *out,
+                             int64_t ld_out);
 
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = default
  * stream).  n_rows must not exceed the reserved chunk size. */

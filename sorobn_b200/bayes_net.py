@@ -221,7 +221,8 @@ class BayesNet:
                                        mode=mode)
             from . import engine  # raises if libsorobn_b200.so cannot be loaded
 
-            hit = (plan, engine.Program(plan, device=self.device))
+            # single-event programs run in float64 (latency-bound anyway); batches in float32
+            hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT)))
             self._engine_cache[key] = hit
         return hit
 
@@ -301,8 +302,15 @@ class BayesNet:
         codes, bad = self._encode_events(ev_vars, [events[v].to_numpy() for v in ev_vars])
         if not ev_vars:
             bad = np.zeros(n, dtype=bool)
-        post = program.run(codes, n)  # [Q, n]
-        out = pd.DataFrame(post.T.astype(np.float64), index=events.index, columns=self._answer_index(plan))
+        post = program.run(codes, n).astype(np.float64)  # [Q, n]
+        # NaN rows: impossible evidence, or a normaliser so small that float32 may have
+        # underflowed -- settle those one by one with the float64 single-event program
+        suspect = np.isnan(post).any(axis=0) & ~bad
+        if suspect.any():
+            _, flat = self._plan(query, ev_vars, _planner.MODE_FLAT)
+            for b in np.nonzero(suspect)[0]:
+                post[:, b] = flat.run(np.ascontiguousarray(codes[:, b:b + 1]), 1)[:, 0]
+        out = pd.DataFrame(post.T, index=events.index, columns=self._answer_index(plan))
         if bad.any():
             out.loc[events.index[bad]] = np.nan
         return out

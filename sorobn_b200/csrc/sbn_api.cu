@@ -80,6 +80,7 @@ int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 struct sbn_program {
     int device = 0;
+    bool f64 = false;  // single-event programs computed and returned in double
     int mode = 0, n_ev = 0, Q = 0, post_slot = 0, post_batched = 0;
     std::vector<std::pair<int64_t, int64_t>> tables;  // (offset, size) in floats
     std::vector<int64_t> table_padded;
@@ -93,7 +94,7 @@ struct sbn_program {
     float *d_shared = nullptr;  // unbatched scratch
     int32_t *d_tile_off = nullptr;  // per-step tile offset tables of the tiled kernel
     uint8_t *d_ev = nullptr;    // staging for run_host  [n_ev][ld]
-    float *d_out = nullptr;     //                         [Q][ld]
+    float *d_out = nullptr;     //                         [Q][ld]   (double when f64)
     cudaStream_t stream = nullptr;
 
     bool use_graph = true;
@@ -367,7 +368,8 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
             d.ptr = P->slots[in.id].ptr;
             padded = P->slots[in.id].padded;
         } else {
-            d.ptr = P->d_tables + P->tables[in.id].first;
+            d.ptr = reinterpret_cast<const float *>(reinterpret_cast<const char *>(P->d_tables) +
+                                                    P->tables[in.id].first * (P->f64 ? 8 : 4));
             padded = P->table_padded[in.id];
         }
         d.batched = in.batched ? 1 : 0;
@@ -543,7 +545,8 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
     if (st.kind == 0) {
         const int threads = 256;
         const int64_t grid = (st.n_out + threads - 1) / threads;
-        sbn_step_flat<<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
+        if (P->f64) sbn_step_flat<double><<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
+        else sbn_step_flat<float><<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
         return cudaGetLastError();
     }
     const int64_t rest = st.n_out / (static_cast<int64_t>(q.n_axes > 0 ? q.card[0] : 1) * (q.n_axes > 1 ? q.card[1] : 1));
@@ -566,8 +569,14 @@ cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64
     P->launches++;
     const int threads = 256;
     const int64_t grid = (n_rows + threads - 1) / threads;
-    sbn_normalise<<<static_cast<unsigned>(grid), threads, 0, stream>>>(P->slots[P->post_slot].ptr, P->ld, P->post_batched,
-                                                                     P->Q, d_out, ld_out, static_cast<int>(n_rows));
+    if (P->f64)
+        sbn_normalise<double><<<static_cast<unsigned>(grid), threads, 0, stream>>>(
+            reinterpret_cast<const double *>(P->slots[P->post_slot].ptr), P->ld, P->post_batched, P->Q,
+            reinterpret_cast<double *>(d_out), ld_out, static_cast<int>(n_rows), 1e-290);
+    else
+        sbn_normalise<float><<<static_cast<unsigned>(grid), threads, 0, stream>>>(
+            P->slots[P->post_slot].ptr, P->ld, P->post_batched, P->Q, d_out, ld_out, static_cast<int>(n_rows),
+            SBN_MIN_TOTAL_F32);
     return cudaGetLastError();
 }
 
@@ -618,13 +627,16 @@ int sbn_device_count(int *count) {
     return SBN_OK;
 }
 
-int sbn_program_create(int device, const int32_t *words, int64_t n_words, const float *tables, int64_t n_table_floats,
-                       sbn_program **out) {
+static int create_common(int device, const int32_t *words, int64_t n_words, const void *tables, int64_t n_table_floats,
+                         bool f64, sbn_program **out) {
     if (!words || !out || (n_table_floats > 0 && !tables)) return fail(SBN_E_INVALID, "null argument");
     *out = nullptr;
     sbn_program *P = new sbn_program();
     P->device = device;
+    P->f64 = f64;
+    const size_t elem = f64 ? 8 : 4;
     int rc = parse(P, words, n_words);
+    if (rc == SBN_OK && f64 && P->mode != 0) rc = fail(SBN_E_INVALID, "float64 programs must be flat (single event)");
     if (rc != SBN_OK) {
         delete P;
         return rc;
@@ -661,20 +673,20 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
                                            device, prop.major, prop.minor));
     SBN_CUDA_P(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     if (n_table_floats > 0) {
-        SBN_CUDA_P(cudaMalloc(&P->d_tables, static_cast<size_t>(n_table_floats) * 4));
-        SBN_CUDA_P(cudaMemcpy(P->d_tables, tables, static_cast<size_t>(n_table_floats) * 4, cudaMemcpyHostToDevice));
+        SBN_CUDA_P(cudaMalloc(&P->d_tables, static_cast<size_t>(n_table_floats) * elem));
+        SBN_CUDA_P(cudaMemcpy(P->d_tables, tables, static_cast<size_t>(n_table_floats) * elem, cudaMemcpyHostToDevice));
     }
     // evidence-independent scratch: one allocation, 256-byte aligned sub-buffers
     int64_t shared_floats = 0;
     for (Slot &s : P->slots)
         if (!s.batched) shared_floats += round_up(s.padded, 64);
     if (shared_floats > 0) {
-        SBN_CUDA_P(cudaMalloc(&P->d_shared, static_cast<size_t>(shared_floats) * 4));
-        SBN_CUDA_P(cudaMemset(P->d_shared, 0, static_cast<size_t>(shared_floats) * 4));
+        SBN_CUDA_P(cudaMalloc(&P->d_shared, static_cast<size_t>(shared_floats) * elem));
+        SBN_CUDA_P(cudaMemset(P->d_shared, 0, static_cast<size_t>(shared_floats) * elem));
         int64_t off = 0;
         for (Slot &s : P->slots)
             if (!s.batched) {
-                s.ptr = P->d_shared + off;
+                s.ptr = reinterpret_cast<float *>(reinterpret_cast<char *>(P->d_shared) + off * elem);
                 off += round_up(s.padded, 64);
             }
     }
@@ -706,6 +718,16 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
 #undef SBN_CUDA_P
     *out = P;
     return SBN_OK;
+}
+
+int sbn_program_create(int device, const int32_t *words, int64_t n_words, const float *tables, int64_t n_table_floats,
+                       sbn_program **out) {
+    return create_common(device, words, n_words, tables, n_table_floats, false, out);
+}
+
+int sbn_program_create_f64(int device, const int32_t *words, int64_t n_words, const double *tables,
+                           int64_t n_table_doubles, sbn_program **out) {
+    return create_common(device, words, n_words, tables, n_table_doubles, true, out);
 }
 
 void sbn_program_destroy(sbn_program *P) {
@@ -756,13 +778,22 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
         SBN_CUDA(cudaMalloc(&P->d_ev, static_cast<size_t>(P->n_ev) * ld));
         SBN_CUDA(cudaMemset(P->d_ev, 0, static_cast<size_t>(P->n_ev) * ld));
     }
-    SBN_CUDA(cudaMalloc(&P->d_out, static_cast<size_t>(P->Q) * ld * 4));
+    SBN_CUDA(cudaMalloc(&P->d_out, static_cast<size_t>(P->Q) * ld * (P->f64 ? 8 : 4)));
     P->reserved_rows = rows;
     P->ld = ld;
     return SBN_OK;
 }
 
+static int run_device_impl(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                           int64_t ld_out, void *stream_);
+
 int sbn_program_run_device(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
+                           int64_t ld_out, void *stream_) {
+    if (P && P->f64) return fail(SBN_E_INVALID, "float64 programs only run through sbn_program_run_host_f64");
+    return run_device_impl(P, d_ev, ld_ev, n_rows, d_out, ld_out, stream_);
+}
+
+static int run_device_impl(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
                            int64_t ld_out, void *stream_) {
     int rc = check_run_args(P, d_ev, ld_ev, n_rows, d_out, ld_out);
     if (rc != SBN_OK) return rc;
@@ -806,9 +837,13 @@ int sbn_program_run_device(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, i
     return SBN_OK;
 }
 
-int sbn_program_run_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out, int64_t ld_out) {
-    int rc = check_run_args(P, ev, ld_ev, n_rows, out, ld_out);
+static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, void *out_, int64_t ld_out,
+                           bool f64) {
+    int rc = check_run_args(P, ev, ld_ev, n_rows, out_, ld_out);
     if (rc != SBN_OK) return rc;
+    if (P->f64 != f64) return fail(SBN_E_INVALID, "program precision does not match the run call");
+    const size_t elem = f64 ? 8 : 4;
+    char *out = static_cast<char *>(out_);
     SBN_CUDA(cudaSetDevice(P->device));
     if (P->reserved_rows == 0) {
         rc = sbn_program_reserve(P, n_rows);
@@ -821,20 +856,30 @@ int sbn_program_run_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64
             SBN_CUDA(cudaMemcpy2DAsync(P->d_ev, static_cast<size_t>(P->ld), ev + r0, static_cast<size_t>(ld_ev),
                                        static_cast<size_t>(rows), static_cast<size_t>(P->n_ev), cudaMemcpyHostToDevice,
                                        P->stream));
-        rc = sbn_program_run_device(P, P->d_ev, P->ld, rows, P->d_out, P->ld, P->stream);
+        rc = run_device_impl(P, P->d_ev, P->ld, rows, P->d_out, P->ld, P->stream);
         if (rc != SBN_OK) return rc;
-        SBN_CUDA(cudaMemcpy2DAsync(out + r0, static_cast<size_t>(ld_out) * 4, P->d_out, static_cast<size_t>(P->ld) * 4,
-                                   static_cast<size_t>(rows) * 4, static_cast<size_t>(P->Q), cudaMemcpyDeviceToHost,
-                                   P->stream));
+        SBN_CUDA(cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, P->d_out,
+                                   static_cast<size_t>(P->ld) * elem, static_cast<size_t>(rows) * elem,
+                                   static_cast<size_t>(P->Q), cudaMemcpyDeviceToHost, P->stream));
     }
     SBN_CUDA(cudaStreamSynchronize(P->stream));
     return SBN_OK;
+}
+
+int sbn_program_run_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out, int64_t ld_out) {
+    return run_host_common(P, ev, ld_ev, n_rows, out, ld_out, false);
+}
+
+int sbn_program_run_host_f64(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *out,
+                             int64_t ld_out) {
+    return run_host_common(P, ev, ld_ev, n_rows, out, ld_out, true);
 }
 
 int sbn_program_profile(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,
                         int64_t ld_out, void *stream_, float *step_ms, int64_t n_step_ms) {
     int rc = check_run_args(P, d_ev, ld_ev, n_rows, d_out, ld_out);
     if (rc != SBN_OK) return rc;
+    if (P->f64) return fail(SBN_E_INVALID, "profiling is for float32 programs");
     const int64_t n = static_cast<int64_t>(P->steps.size()) + 1;
     if (!step_ms || n_step_ms < n) return fail(SBN_E_INVALID, "step_ms needs %lld entries", (long long)n);
     SBN_CUDA(cudaSetDevice(P->device));

@@ -555,6 +555,9 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
 // Evidence-independent factors (and single-row "flat" programs): one thread per
 // output entry, mixed-radix decomposition of the entry index in registers, the
 // eliminated axis reduced in-thread.  Evidence offsets are uniform (row 0).
+// T = float inside batched programs, double for single-event programs (those are
+// launch-latency bound, so they get the reference's own precision and range for free).
+template <typename T>
 __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ SbnStep p) {
     const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (o >= p.n_out) return;
@@ -578,28 +581,36 @@ __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ Sbn
         for (int i = 0; i < SBN_MAX_IN; ++i)
             if (i < p.n_in) off[i] += d * p.in[i].stride[j];
     }
-    float acc = 0.f;
+    T acc = T(0);
     for (int x = 0; x < p.cx; ++x) {
-        float prod = 1.f;
+        T prod = T(1);
 #pragma unroll
         for (int i = 0; i < SBN_MAX_IN; ++i)
-            if (i < p.n_in) prod *= __ldg(p.in[i].ptr + off[i] + x * p.in[i].sx);
+            if (i < p.n_in) prod *= __ldg(reinterpret_cast<const T *>(p.in[i].ptr) + off[i] + x * p.in[i].sx);
         acc += prod;
     }
-    p.out[o] = acc;
+    reinterpret_cast<T *>(p.out)[o] = acc;
 }
 
 // ---------------------------------------------------------------------- normalise
 // posterior[q, b] = post[q, b] / sum_q post[q, b]   (bayes_net.py:789-790)
 // One thread per evidence row; reads are coalesced across rows for every q.
+// Rows whose normaliser is below SBN_MIN_TOTAL (zero for impossible evidence, or so small
+// that fp32 underflow may have eaten addends) are written as NaN: the caller re-runs them in
+// float64 (BayesNet.query_many does) or treats them as impossible evidence.
+#define SBN_MIN_TOTAL_F32 1e-24f
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-sbn_normalise(const float *__restrict__ post, int64_t ld, int post_batched, int Q, float *__restrict__ out,
-              int64_t ld_out, int n_rows) {
+sbn_normalise(const T *__restrict__ post, int64_t ld, int post_batched, int Q, T *__restrict__ out, int64_t ld_out,
+              int n_rows, T min_total) {
     const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= n_rows) return;
-    const int64_t pitch = post_batched ? ld : 0;
+    const int64_t pitch = post_batched ? ld : 1;
     const int64_t base = post_batched ? b : 0;
-    float total = 0.f;
-    for (int q = 0; q < Q; ++q) total += post[q * (post_batched ? pitch : 1) + base];
-    for (int q = 0; q < Q; ++q) out[q * ld_out + b] = post[q * (post_batched ? pitch : 1) + base] / total;
+    T total = T(0);
+    for (int q = 0; q < Q; ++q) total += post[q * pitch + base];
+    const bool ok = total >= min_total;  // false for NaN too
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    for (int q = 0; q < Q; ++q) out[q * ld_out + b] = ok ? post[q * pitch + base] / total : nan;
 }

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class EngineError(RuntimeError):
@@ -49,6 +49,10 @@ def load():
     lib.sbn_device_count.argtypes = [c.POINTER(i32)]
     lib.sbn_program_create.restype = i32
     lib.sbn_program_create.argtypes = [i32, vp, i64, vp, i64, c.POINTER(vp)]
+    lib.sbn_program_create_f64.restype = i32
+    lib.sbn_program_create_f64.argtypes = [i32, vp, i64, vp, i64, c.POINTER(vp)]
+    lib.sbn_program_run_host_f64.restype = i32
+    lib.sbn_program_run_host_f64.argtypes = [vp, vp, i64, i64, vp, i64]
     lib.sbn_program_destroy.restype = None
     lib.sbn_program_destroy.argtypes = [vp]
     lib.sbn_program_reserve.restype = i32
@@ -76,7 +80,8 @@ def load():
 
 
 EXPORTS = (
-    "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_destroy",
+    "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_create_f64",
+    "sbn_program_run_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
     "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_host_alloc", "sbn_host_free",
 )
@@ -126,14 +131,20 @@ class PinnedArray:
 class Program:
     """One compiled (query variables, evidence variables) pair on one GPU."""
 
-    def __init__(self, plan, device: int | None = None):
+    def __init__(self, plan, device: int | None = None, f64: bool = False):
         lib = load()
         self.plan = plan
         self.device = default_device() if device is None else int(device)
         self.Q = int(plan.Q)
         self.n_ev = len(plan.evidence)
+        self.f64 = bool(f64)
         self._h = ctypes.c_void_p()
         words = np.ascontiguousarray(plan.words, dtype=np.int32)
+        if self.f64:
+            blob = np.ascontiguousarray(plan.table_blob64, dtype=np.float64)
+            _check(lib.sbn_program_create_f64(self.device, words.ctypes.data, words.size, blob.ctypes.data, blob.size,
+                                              ctypes.byref(self._h)))
+            return
         blob = np.ascontiguousarray(plan.table_blob, dtype=np.float32)
         _check(lib.sbn_program_create(self.device, words.ctypes.data, words.size, blob.ctypes.data, blob.size,
                                       ctypes.byref(self._h)))
@@ -181,12 +192,14 @@ class Program:
         if self.n_ev:
             if codes.shape != (self.n_ev, n_rows):
                 raise ValueError(f"evidence codes have shape {codes.shape}, expected {(self.n_ev, n_rows)}")
+        dtype = np.float64 if self.f64 else np.float32
         if out is None:
-            out = np.empty((self.Q, n_rows), dtype=np.float32)
-        elif out.shape != (self.Q, n_rows) or out.dtype != np.float32 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous float32 [Q, n_rows] array")
+            out = np.empty((self.Q, n_rows), dtype=dtype)
+        elif out.shape != (self.Q, n_rows) or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous {dtype.__name__} [Q, n_rows] array")
         ev_ptr = codes.ctypes.data if self.n_ev else None
-        _check(load().sbn_program_run_host(self._h, ev_ptr, n_rows, n_rows, out.ctypes.data, n_rows))
+        fn = load().sbn_program_run_host_f64 if self.f64 else load().sbn_program_run_host
+        _check(fn(self._h, ev_ptr, n_rows, n_rows, out.ctypes.data, n_rows))
         return out
 
     def run_device(self, d_ev: int, ld_ev: int, n_rows: int, d_out: int, ld_out: int, stream: int = 0):

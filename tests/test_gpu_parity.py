@@ -302,3 +302,46 @@ def test_device_pointer_api_matches_host_api():
         assert np.array_equal(d_out.cpu().numpy(), want)
     info = prog.info()
     assert info["launches"] > 0 and info["Q"] == 2 and info["n_ev"] == 4
+
+
+def test_single_queries_run_in_float64():
+    """`query()` programs are float64 on the device: reference-grade precision (1e-12 here,
+    against 1e-6 for the float32 batch path) on every example golden."""
+    golden = load_golden("asia")
+    bn = build_network(golden)
+    worst = 0.0
+    for case in golden["cases"][::7]:
+        ans = bn.query(*case["query"], event=case_event(case))
+        if case["values"]:
+            worst = max(worst, rel_err(ans.to_numpy(), case["values"]))
+    assert worst < 1e-12, worst
+
+
+def test_extremely_unlikely_evidence_is_rescued_in_float64():
+    """A 120-node chain observed at 119 nodes with near-deterministic CPTs: the evidence has
+    probability ~1e-240, far below float32.  The float32 batch flags the row (normaliser <
+    1e-24) and query_many settles it with the float64 program; the reference (float64) and
+    the oracle agree with the result."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet
+
+    n = 120
+    names = [f"c{k:03d}" for k in range(n)]
+    bn = BayesNet(*[(names[k - 1], names[k]) for k in range(1, n)])
+    bn.P[names[0]] = pd.Series({0: 0.5, 1: 0.5})
+    for k in range(1, n):
+        bn.P[names[k]] = pd.DataFrame({names[k - 1]: [0, 0, 1, 1], names[k]: [0, 1, 0, 1],
+                                       "p": [0.99, 0.01, 0.02, 0.98]})
+    bn.prepare()
+    # alternate the observed states: every transition is the unlikely one
+    ev_vars = names[1:]
+    rows = pd.DataFrame([[k % 2 for k in range(1, n)], [0] * (n - 1)], columns=ev_vars)
+    got = bn.query_many(names[0], events=rows).to_numpy()
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    for b in range(2):
+        ev = {v: int(rows[v].iloc[b]) for v in ev_vars}
+        want = ve_oracle.query(dn, names[0], event=ev)[1].reshape(-1)
+        assert np.isfinite(got[b]).all()
+        assert rel_err(got[b], want) < 1e-9, (b, got[b], want)
+    single = bn.query(names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})
+    assert rel_err(single.to_numpy(), ve_oracle.query(dn, names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})[1]) < 1e-12

@@ -156,7 +156,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = engine.load()
     assert lib.sbn_abi_version() == engine.ABI_VERSION
     header = open(os.path.join(ROOT, "include", "sorobn_b200.h")).read()
-    declared = set(re.findall(r"\b(sbn_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(sbn_[a-z0-9_]+)\s*\(", header))
     assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
     raw = ctypes.CDLL(engine.lib_path())
     for name in declared:
