@@ -27,7 +27,7 @@
  * name and the last one varying fastest -- the row order of the reference's answer
  * (`reorder_levels(sorted(...))`, `sort_index()`; bayes_net.py:872-875).
  * A row whose evidence has probability zero yields NaN (the reference returns an
- * empty Series there).  In float32 programs a row whose normaliser is below 1e-24 is also
+ * empty Series there).  In float32 programs a row whose normaliser is below 1e-30 is also
  * NaN: float32 underflow may have dropped addends; re-run it with a float64 program.
  *
  * Every function returns 0 on success or a negative SBN_E_* code;

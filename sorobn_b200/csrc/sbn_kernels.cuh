@@ -263,11 +263,14 @@ __device__ __forceinline__ void sbn_ldv(float (&r)[V], const float *ptr) {
     const typename SbnVec<V>::type t = *reinterpret_cast<const typename SbnVec<V>::type *>(ptr);
     memcpy(r, &t, sizeof t);
 }
+// Streaming store (st.global.cs, evict-first): an output is next read by a later launch,
+// after hundreds of MB of other traffic, so it should not displace from L2 the operands
+// that co-resident CTAs are about to re-read.
 template <int V>
 __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
     typename SbnVec<V>::type t;
     memcpy(&t, r, sizeof t);
-    *reinterpret_cast<typename SbnVec<V>::type *>(ptr) = t;
+    __stcs(reinterpret_cast<typename SbnVec<V>::type *>(ptr), t);
 }
 
 #define SBN_TILED_THREADS 128
@@ -598,7 +601,11 @@ __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ Sbn
 // Rows whose normaliser is below SBN_MIN_TOTAL (zero for impossible evidence, or so small
 // that fp32 underflow may have eaten addends) are written as NaN: the caller re-runs them in
 // float64 (BayesNet.query_many does) or treats them as impossible evidence.
-#define SBN_MIN_TOTAL_F32 1e-24f
+// Why 1e-30 is safe: every factor entry is <= 1, so an intermediate entry that contributes
+// more than 1e-7 of a normaliser T >= 1e-30 is itself >= 1e-37, i.e. a normal fp32 number
+// carrying full precision; what underflowed is bounded by ~1e5 operations x 1.4e-45
+// (the denormal quantum) = 1e-40 absolute, 1e-10 relative to T.
+#define SBN_MIN_TOTAL_F32 1e-30f
 
 template <typename T>
 __global__ void __launch_bounds__(256)

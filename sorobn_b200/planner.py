@@ -217,7 +217,7 @@ def table_scale_log2(table: np.ndarray) -> int:
     <= 1 (when a variable is eliminated its own CPT, which sums to one over it, is in
     the product and every other entry is <= 1 by induction), so fp32 can never
     overflow.  What can happen is underflow when the evidence is astronomically
-    unlikely (P(event) < ~1e-24); the engine detects that per row from the normaliser
+    unlikely (P(event) < ~1e-30); the engine detects that per row from the normaliser
     (DESIGN.md "fp32 range").  The hook stays because a per-table power of two is exact
     and cancels in the normalisation (bayes_net.py:790)."""
     return 0

@@ -342,6 +342,7 @@ def test_extremely_unlikely_evidence_is_rescued_in_float64():
         ev = {v: int(rows[v].iloc[b]) for v in ev_vars}
         want = ve_oracle.query(dn, names[0], event=ev)[1].reshape(-1)
         assert np.isfinite(got[b]).all()
-        assert rel_err(got[b], want) < 1e-9, (b, got[b], want)
+        # row 0 (P(event) ~ 1e-240) was settled in float64, row 1 stayed in float32
+        assert rel_err(got[b], want) < (1e-9 if b == 0 else RTOL), (b, got[b], want)
     single = bn.query(names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})
     assert rel_err(single.to_numpy(), ve_oracle.query(dn, names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})[1]) < 1e-12
