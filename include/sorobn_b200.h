@@ -105,7 +105,9 @@ int sbn_program_profile(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, i
  * [7]=unbatched scratch floats */
 int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 
-/* Toggle CUDA-graph replay of the step sequence (default on). */
+/* 0 = plain launches; 1 = CUDA-graph replay of the step sequence (default); 3 = graph replay
+ * with independent sub-trees of the elimination as parallel branches (experimental: measured
+ * no gain on the benchmark plans, which are one long dependency chain). */
 int sbn_program_set_graph(sbn_program *prog, int enabled);
 
 /* Select the step kernel: 0 = the plain one-output-per-iteration kernel (general

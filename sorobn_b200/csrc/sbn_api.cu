@@ -96,6 +96,13 @@ struct sbn_program {
     uint8_t *d_ev = nullptr;    // staging for run_host  [n_ev][ld]
     float *d_out = nullptr;     //                         [Q][ld]   (double when f64)
     cudaStream_t stream = nullptr;
+    // Branch streams for graph capture: the steps form a tree (every intermediate is consumed
+    // once), so independent sub-trees are captured on different streams and become parallel
+    // branches of the CUDA graph.
+    static constexpr int kBranches = 4;
+    cudaStream_t branch[kBranches] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> step_done;  // one event per step (+ normalise), capture-only
+    bool use_branches = false;  // measured: no gain on the grid plan (one long chain); opt-in
 
     bool use_graph = true;
     bool use_tiled = true;
@@ -596,6 +603,71 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
     return SBN_OK;
 }
 
+// Capture-time variant of issue_all: steps are spread over the branch streams and ordered
+// by events, so the instantiated graph carries exactly the true dependencies:
+//   * read-after-write: a step waits for the producers of its slot inputs;
+//   * slot reuse: a step that overwrites a slot waits for the slot's previous writer and
+//     for every reader of the previous tenant.
+// A step runs on the stream of the producer of its largest slot input (chains stay on one
+// stream, no event needed); leaves take the branch streams round-robin.
+int issue_branched(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out, int64_t ld_out,
+                   cudaStream_t origin) {
+    const int n_steps = static_cast<int>(P->steps.size());
+    const int n_slots = static_cast<int>(P->slots.size());
+    std::vector<int> last_writer(n_slots, -1);
+    std::vector<std::vector<int>> readers(n_slots);
+    std::vector<int> stream_of(n_steps, 0);
+    cudaEvent_t fork = P->step_done[n_steps];  // reused as the fork event before any step
+    SBN_CUDA(cudaEventRecord(fork, origin));
+    bool joined[sbn_program::kBranches] = {false, false, false, false};
+    int rr = 0;
+    SbnStep q;
+    for (int s = 0; s < n_steps; ++s) {
+        const StepDesc &st = P->steps[s];
+        std::vector<int> deps;
+        int home = -1;
+        int64_t home_size = -1;
+        for (const InDesc &in : st.in) {
+            if (!in.is_slot) continue;
+            const int w = last_writer[in.id];
+            if (w >= 0) {
+                deps.push_back(w);
+                if (P->slots[in.id].size > home_size) {
+                    home_size = P->slots[in.id].size;
+                    home = stream_of[w];
+                }
+            }
+        }
+        if (last_writer[st.out_slot] >= 0) deps.push_back(last_writer[st.out_slot]);
+        for (int r : readers[st.out_slot]) deps.push_back(r);
+        const int k = home >= 0 ? home : (rr++ % sbn_program::kBranches);
+        stream_of[s] = k;
+        cudaStream_t stream = P->branch[k];
+        if (!joined[k]) {
+            SBN_CUDA(cudaStreamWaitEvent(stream, fork, 0));
+            joined[k] = true;
+        }
+        std::sort(deps.begin(), deps.end());
+        deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+        for (int d : deps)
+            if (stream_of[d] != k) SBN_CUDA(cudaStreamWaitEvent(stream, P->step_done[d], 0));
+        build_params(P, st, d_ev, ld_ev, n_rows, &q);
+        SBN_CUDA(launch_step(P, st, q, stream));
+        SBN_CUDA(cudaEventRecord(P->step_done[s], stream));
+        for (const InDesc &in : st.in)
+            if (in.is_slot) readers[in.id].push_back(s);
+        last_writer[st.out_slot] = s;
+        readers[st.out_slot].clear();
+    }
+    // join: the origin stream waits for the tail of every branch that was used, then normalises
+    std::vector<int> tail(sbn_program::kBranches, -1);
+    for (int s = 0; s < n_steps; ++s) tail[stream_of[s]] = s;
+    for (int k = 0; k < sbn_program::kBranches; ++k)
+        if (tail[k] >= 0) SBN_CUDA(cudaStreamWaitEvent(origin, P->step_done[tail[k]], 0));
+    SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, origin));
+    return SBN_OK;
+}
+
 int check_run_args(sbn_program *P, const void *ev, int64_t ld_ev, int64_t n_rows, const void *out, int64_t ld_out) {
     if (!P) return fail(SBN_E_INVALID, "null program");
     if (n_rows <= 0) return fail(SBN_E_INVALID, "n_rows must be positive");
@@ -672,9 +744,17 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
     if (prop.major != 10) return bail(fail(SBN_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                                            device, prop.major, prop.minor));
     SBN_CUDA_P(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < sbn_program::kBranches; ++k)
+        SBN_CUDA_P(cudaStreamCreateWithFlags(&P->branch[k], cudaStreamNonBlocking));
+    P->step_done.resize(P->steps.size() + 1);
+    for (auto &e : P->step_done) SBN_CUDA_P(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (n_table_floats > 0) {
+        // All setup traffic goes through the program's own (non-blocking) stream and is
+        // synchronised below: a NULL-stream cudaMemcpy from pageable memory may return before
+        // the DMA lands and would not be ordered with later work on P->stream.
         SBN_CUDA_P(cudaMalloc(&P->d_tables, static_cast<size_t>(n_table_floats) * elem));
-        SBN_CUDA_P(cudaMemcpy(P->d_tables, tables, static_cast<size_t>(n_table_floats) * elem, cudaMemcpyHostToDevice));
+        SBN_CUDA_P(cudaMemcpyAsync(P->d_tables, tables, static_cast<size_t>(n_table_floats) * elem,
+                                   cudaMemcpyHostToDevice, P->stream));
     }
     // evidence-independent scratch: one allocation, 256-byte aligned sub-buffers
     int64_t shared_floats = 0;
@@ -682,7 +762,7 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
         if (!s.batched) shared_floats += round_up(s.padded, 64);
     if (shared_floats > 0) {
         SBN_CUDA_P(cudaMalloc(&P->d_shared, static_cast<size_t>(shared_floats) * elem));
-        SBN_CUDA_P(cudaMemset(P->d_shared, 0, static_cast<size_t>(shared_floats) * elem));
+        SBN_CUDA_P(cudaMemsetAsync(P->d_shared, 0, static_cast<size_t>(shared_floats) * elem, P->stream));
         int64_t off = 0;
         for (Slot &s : P->slots)
             if (!s.batched) {
@@ -695,8 +775,11 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
         plan_tiles(P, &tile_words);
         if (!tile_words.empty()) {
             SBN_CUDA_P(cudaMalloc(&P->d_tile_off, tile_words.size() * 4));
-            SBN_CUDA_P(cudaMemcpy(P->d_tile_off, tile_words.data(), tile_words.size() * 4, cudaMemcpyHostToDevice));
+            SBN_CUDA_P(cudaMemcpyAsync(P->d_tile_off, tile_words.data(), tile_words.size() * 4,
+                                       cudaMemcpyHostToDevice, P->stream));
         }
+        // tile_words goes out of scope here: the copy must have consumed it
+        SBN_CUDA_P(cudaStreamSynchronize(P->stream));
     }
     {
         // opt every step-kernel instantiation into SBN_SMEM_BUDGET of dynamic shared memory
@@ -738,6 +821,10 @@ void sbn_program_destroy(sbn_program *P) {
     cudaFree(P->d_tile_off);
     cudaFree(P->d_tables);
     if (P->stream) cudaStreamDestroy(P->stream);
+    for (auto &b : P->branch)
+        if (b) cudaStreamDestroy(b);
+    for (auto &e : P->step_done)
+        if (e) cudaEventDestroy(e);
     delete P;
 }
 
@@ -776,9 +863,10 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
     }
     if (P->n_ev > 0) {
         SBN_CUDA(cudaMalloc(&P->d_ev, static_cast<size_t>(P->n_ev) * ld));
-        SBN_CUDA(cudaMemset(P->d_ev, 0, static_cast<size_t>(P->n_ev) * ld));
+        SBN_CUDA(cudaMemsetAsync(P->d_ev, 0, static_cast<size_t>(P->n_ev) * ld, P->stream));
     }
     SBN_CUDA(cudaMalloc(&P->d_out, static_cast<size_t>(P->Q) * ld * (P->f64 ? 8 : 4)));
+    SBN_CUDA(cudaStreamSynchronize(P->stream));  // the memset must not race a caller's stream
     P->reserved_rows = rows;
     P->ld = ld;
     return SBN_OK;
@@ -817,7 +905,8 @@ static int run_device_impl(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, i
         cudaStream_t cap = P->stream;  // capture on the program's own stream, replay on the caller's
         SBN_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
         const int64_t before = P->launches;
-        rc = issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, cap, nullptr);
+        rc = P->use_branches ? issue_branched(P, d_ev, ld_ev, n_rows, d_out, ld_out, cap)
+                             : issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, cap, nullptr);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(cap, &graph);
         P->graph_launches = P->launches - before;
@@ -921,6 +1010,11 @@ int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
 int sbn_program_set_graph(sbn_program *P, int enabled) {
     if (!P) return fail(SBN_E_INVALID, "null program");
     P->use_graph = enabled != 0;
+    P->use_branches = enabled == 3;
+    if (P->exec) {
+        cudaGraphExecDestroy(P->exec);
+        P->exec = nullptr;
+    }
     return SBN_OK;
 }
 

@@ -346,3 +346,24 @@ def test_extremely_unlikely_evidence_is_rescued_in_float64():
         assert rel_err(got[b], want) < (1e-9 if b == 0 else RTOL), (b, got[b], want)
     single = bn.query(names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})
     assert rel_err(single.to_numpy(), ve_oracle.query(dn, names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})[1]) < 1e-12
+
+
+def test_graph_branches_match_linear_replay_and_plain_launches():
+    """The branched CUDA graph (independent elimination sub-trees in parallel, slot-reuse
+    hazards as edges) must give bitwise the same posteriors as the linear graph and as
+    plain launches, repeatedly (a missing edge would show up as a race)."""
+    from sorobn_b200 import engine, planner, workloads
+
+    for wl, B in ((workloads.grid10x10(), 20_000), (workloads.dag50(), 5_000), (workloads.asia_1m(), 50_000)):
+        bn = wl.build()
+        net = bn._compiled
+        plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+        prog = engine.Program(plan)
+        codes = wl.codes(bn, B, seed=21)
+        prog.set_graph(0)
+        want = prog.run(codes, B).copy()
+        assert np.isfinite(want).all()
+        for mode in (1, 3, 1):
+            prog.set_graph(mode)
+            for _ in range(3):
+                assert np.array_equal(prog.run(codes, B), want), (wl.name, mode)
