@@ -34,22 +34,26 @@ def parse(words):
         p += 2
     steps = []
     for _ in range(hdr["n_steps"]):
-        kind, n_in, out_slot, n_axes, cx = w[p:p + 5]
+        kind, n_in, out_slot, n_axes, n_elim = w[p:p + 5]
         p += 5
         cards = w[p:p + n_axes]
         p += n_axes
+        ecards = w[p:p + n_elim]
+        p += n_elim
         ins = []
         for _ in range(n_in):
-            is_slot, buf, batched, sx, n_ev = w[p:p + 5]
-            p += 5
+            is_slot, buf, batched, n_ev = w[p:p + 4]
+            p += 4
             ev = []
             for _ in range(n_ev):
                 ev.append((w[p], w[p + 1], w[p + 2]))
                 p += 3
+            estrides = w[p:p + n_elim]
+            p += n_elim
             strides = w[p:p + n_axes]
             p += n_axes
-            ins.append(dict(is_slot=is_slot, buf=buf, batched=batched, sx=sx, ev=ev, strides=strides))
-        steps.append(dict(kind=kind, out_slot=out_slot, cards=cards, cx=cx, inputs=ins))
+            ins.append(dict(is_slot=is_slot, buf=buf, batched=batched, estrides=estrides, ev=ev, strides=strides))
+        steps.append(dict(kind=kind, out_slot=out_slot, cards=cards, ecards=ecards, inputs=ins))
     assert p == len(w), (p, len(w))
     return hdr, tables, slots, steps
 
@@ -86,13 +90,19 @@ def run(words, table_blob, ev_codes, n_rows=None, dtype=np.float64):
         assert all(not (i["is_slot"] and i["buf"] == st["out_slot"]) for i in st["inputs"]), "output aliases an input"
         rows = B if (batched_out or hdr["mode"] == 0) else 1
         acc = np.zeros((n_out, rows), dtype=dtype)
-        for x in range(st["cx"]):
+        cx = int(np.prod(st["ecards"], dtype=np.int64)) if st["ecards"] else 1
+        for x in range(cx):
+            # joint state x of the eliminated variables, first variable fastest
+            xd, rem_x = [], x
+            for c in st["ecards"]:
+                xd.append(rem_x % c)
+                rem_x //= c
             prod = np.ones((n_out, rows), dtype=dtype)
             for inp in st["inputs"]:
                 off = np.zeros(n_out, dtype=np.int64)
                 for d, s in zip(digits, inp["strides"]):
                     off += d * s
-                off = off + x * inp["sx"]
+                off = off + sum(d * s for d, s in zip(xd, inp["estrides"]))
                 evoff = np.zeros(rows, dtype=np.int64)
                 for col, s, c in inp["ev"]:
                     evoff = evoff + np.minimum(ev_codes[col, :rows].astype(np.int64), c - 1) * s

@@ -39,7 +39,9 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int32_t kMagic = 0x53424E31;
-constexpr int kVersion = 3;
+constexpr int kVersion = 4;
+constexpr int kMaxElim = 3;
+constexpr int kMaxZ = 256;
 constexpr int kHeaderWords = 12;
 
 struct EvAxis {
@@ -49,16 +51,19 @@ struct InDesc {
     bool is_slot;
     int id;
     bool batched;
-    int sx;
+    int sx;                      // stride of the eliminated axis when there is exactly one
     std::vector<EvAxis> ev;
+    std::vector<int> estrides;   // stride per eliminated axis
     std::vector<int> strides;
 };
 struct StepDesc {
     int kind;
     int out_slot;
-    int cx;
+    int cx;                      // joint states of the eliminated variables (1 = product only)
     int64_t n_out;
     std::vector<int> cards;
+    std::vector<int> ecards;     // cardinality per eliminated variable
+    int64_t zoff_pos = -1;       // >= 0: int32 offset of the [n_in][cx] joint-state offset table
     std::vector<InDesc> in;
     // tiled fast path (sbn_step_tiled): tile edge, tile count, offset-table position
     int tile = 0;            // 0 = not eligible, use sbn_step_batched
@@ -162,15 +167,16 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
         const int n_in = w[p + 1];
         st.out_slot = w[p + 2];
         const int n_axes = w[p + 3];
-        st.cx = w[p + 4];
+        const int n_elim = w[p + 4];
+        st.cx = 1;
         p += 5;
         if (st.kind != 0 && st.kind != 1) return fail(SBN_E_INVALID, "step %d: bad kind", s);
         if (st.kind == 1 && P->mode == 0) return fail(SBN_E_INVALID, "step %d: batched step in a flat program", s);
         if (n_in < 1 || n_in > SBN_MAX_IN) return fail(SBN_E_INVALID, "step %d: %d inputs", s, n_in);
         if (n_axes < 0 || n_axes > SBN_MAX_AXES) return fail(SBN_E_INVALID, "step %d: %d axes", s, n_axes);
-        if (st.cx < 1) return fail(SBN_E_INVALID, "step %d: cx %d", s, st.cx);
+        if (n_elim < 0 || n_elim > kMaxElim) return fail(SBN_E_INVALID, "step %d: %d eliminated axes", s, n_elim);
         if (st.out_slot < 0 || st.out_slot >= n_slots) return fail(SBN_E_INVALID, "step %d: out slot", s);
-        if (!need(n_axes)) return fail(SBN_E_INVALID, "truncated step %d", s);
+        if (!need(n_axes + n_elim)) return fail(SBN_E_INVALID, "truncated step %d", s);
         st.n_out = 1;
         for (int j = 0; j < n_axes; ++j) {
             const int c = w[p + j];
@@ -180,20 +186,28 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
             st.cards.push_back(c);
         }
         p += n_axes;
+        for (int k = 0; k < n_elim; ++k) {
+            const int c = w[p + k];
+            if (c < 1) return fail(SBN_E_INVALID, "step %d: eliminated card %d", s, c);
+            if (static_cast<int64_t>(st.cx) * c > kMaxZ) return fail(SBN_E_INVALID, "step %d: too many eliminated states", s);
+            st.cx *= c;
+            st.ecards.push_back(c);
+        }
+        p += n_elim;
         const Slot &os = P->slots[st.out_slot];
         if (os.batched != (st.kind == 1)) return fail(SBN_E_INVALID, "step %d: out slot kind mismatch", s);
         if (os.size < st.n_out) return fail(SBN_E_INVALID, "step %d: out slot too small", s);
         for (int i = 0; i < n_in; ++i) {
-            if (!need(5)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
+            if (!need(4)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
             InDesc in;
             in.is_slot = w[p] != 0;
             in.id = w[p + 1];
             in.batched = w[p + 2] != 0;
-            in.sx = w[p + 3];
-            const int n_ev = w[p + 4];
-            p += 5;
+            in.sx = 0;
+            const int n_ev = w[p + 3];
+            p += 4;
             if (n_ev < 0 || n_ev > SBN_MAX_EV) return fail(SBN_E_INVALID, "step %d input %d: %d ev axes", s, i, n_ev);
-            if (!need(3LL * n_ev + n_axes)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
+            if (!need(3LL * n_ev + n_elim + n_axes)) return fail(SBN_E_INVALID, "truncated step %d input %d", s, i);
             int64_t size;
             if (in.is_slot) {
                 if (in.id < 0 || in.id >= n_slots) return fail(SBN_E_INVALID, "step %d input %d: slot id", s, i);
@@ -210,8 +224,7 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
             if (in.batched && n_ev) return fail(SBN_E_INVALID, "step %d input %d: batched input with ev axes", s, i);
             if (n_ev && st.kind != 1 && P->mode != 0)
                 return fail(SBN_E_INVALID, "step %d input %d: evidence axes in an unbatched step", s, i);
-            if (in.sx < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
-            int64_t max_off = static_cast<int64_t>(st.cx - 1) * in.sx;
+            int64_t max_off = 0;
             for (int k = 0; k < n_ev; ++k) {
                 EvAxis a{w[p], w[p + 1], w[p + 2]};
                 p += 3;
@@ -220,6 +233,14 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
                 max_off += static_cast<int64_t>(a.card - 1) * a.stride;
                 in.ev.push_back(a);
             }
+            for (int k = 0; k < n_elim; ++k) {
+                const int sk = w[p + k];
+                if (sk < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
+                max_off += static_cast<int64_t>(st.ecards[k] - 1) * sk;
+                in.estrides.push_back(sk);
+            }
+            p += n_elim;
+            if (n_elim == 1) in.sx = in.estrides[0];
             for (int j = 0; j < n_axes; ++j) {
                 const int sj = w[p + j];
                 if (sj < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
@@ -245,9 +266,28 @@ constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 // output entry and each input's element offset (the row-invariant mixed-radix
 // decomposition, hoisted out of the kernel).
 void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
+    // joint-state offset tables of the steps that sum out several variables at once:
+    // zoff[i][z] = sum_k digit_k(z) * estride_i[k], first eliminated variable fastest
+    for (StepDesc &st : P->steps) {
+        st.zoff_pos = -1;
+        if (st.ecards.size() < 2) continue;
+        st.zoff_pos = static_cast<int64_t>(words->size());
+        for (const InDesc &in : st.in) {
+            for (int z = 0; z < st.cx; ++z) {
+                int r = z;
+                int64_t off = 0;
+                for (size_t k = 0; k < st.ecards.size(); ++k) {
+                    off += static_cast<int64_t>(r % st.ecards[k]) * in.estrides[k];
+                    r /= st.ecards[k];
+                }
+                words->push_back(static_cast<int32_t>(off));
+            }
+        }
+    }
     for (StepDesc &st : P->steps) {
         st.tile = 0;
         if (st.kind != 1 || st.in.size() > static_cast<size_t>(kTiledMaxIn)) continue;
+        if (st.ecards.size() > 1) continue;  // several eliminated axes: plain kernel
         int64_t smem = 0;
         for (const InDesc &in : st.in)
             if (!in.batched) smem += in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
@@ -363,6 +403,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     q->n_in = static_cast<int32_t>(st.in.size());
     q->n_axes = static_cast<int32_t>(st.cards.size());
     q->cx = st.cx;
+    q->zoff = st.zoff_pos >= 0 ? P->d_tile_off + st.zoff_pos : nullptr;
     q->n_out = static_cast<int32_t>(st.n_out);
     for (size_t j = 0; j < st.cards.size(); ++j) q->card[j] = st.cards[j];
     int smem = 0;

@@ -60,6 +60,8 @@ struct SbnStep {
     const int32_t *tile_off;          // tiled kernel: [n_tiles][n_in + 2] = out entry, na | nb << 8, input offsets
     int32_t n_tiles;
     int32_t n_chunks;                 // tiled kernel: ceil(n_tiles / tiles_per_cta)
+    const int32_t *zoff;              // several eliminated variables: [n_in][cx] element offsets of
+                                      // their joint states (nullptr: one variable, offset = x * sx)
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_con
                 float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
                 for (int i = 0; i < N_IN; ++i) {
-                    const int e = e0[i] + x * p.in[i].sx;
+                    const int e = e0[i] + (p.zoff ? __ldg(p.zoff + i * cx + x) : x * p.in[i].sx);
                     float4 v;
                     if (p.in[i].batched) {
                         v = *reinterpret_cast<const float4 *>(p.in[i].ptr + static_cast<int64_t>(e) * ld + b);
@@ -589,7 +591,9 @@ __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ Sbn
         T prod = T(1);
 #pragma unroll
         for (int i = 0; i < SBN_MAX_IN; ++i)
-            if (i < p.n_in) prod *= __ldg(reinterpret_cast<const T *>(p.in[i].ptr) + off[i] + x * p.in[i].sx);
+            if (i < p.n_in)
+                prod *= __ldg(reinterpret_cast<const T *>(p.in[i].ptr) + off[i] +
+                              (p.zoff ? __ldg(p.zoff + i * p.cx + x) : x * p.in[i].sx));
         acc += prod;
     }
     reinterpret_cast<T *>(p.out)[o] = acc;

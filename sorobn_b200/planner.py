@@ -29,8 +29,13 @@ oracle/program_interp.py (the CPU checker used in tests):
     header : MAGIC VERSION mode n_ev n_tables n_slots n_steps Q post_slot post_batched 0 0
     tables : (offset_floats, size) * n_tables         -- into the float table blob
     slots  : (batched, size_per_row) * n_slots        -- scratch buffers
-    steps  : kind n_in out_slot n_axes cX | cards[n_axes] |
-             per input: is_slot id batched sx n_ev (col stride card)*n_ev strides[n_axes]
+    steps  : kind n_in out_slot n_axes n_elim | cards[n_axes] | ecards[n_elim] |
+             per input: is_slot id batched n_ev (col stride card)*n_ev estrides[n_elim] strides[n_axes]
+
+A step sums out `n_elim` variables at once (0 = product only): the reference's
+`sum_out(*variables)` (bayes_net.py:54) also takes several.  The planner folds a pure
+sum-out (an elimination whose only factor is the previous product) into its producer, which
+saves writing and re-reading the intermediate.
 
 `mode` 0 = flat (one evidence row, nothing batched: evidence offsets are uniform),
 1 = batched.  The posterior is produced by the last step into `post_slot`
@@ -43,11 +48,13 @@ from dataclasses import dataclass, field
 import numpy as np
 
 MAGIC = 0x53424E31  # "SBN1"
-VERSION = 3
+VERSION = 4
 MAX_IN = 8  # factors fused per launch (csrc/sbn_kernels.cuh: SBN_MAX_IN)
 MAX_AXES = 20  # output axes per step (SBN_MAX_AXES)
 MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
 TILE_EDGE = 5  # largest register-tile edge of sbn_step_tiled
+MAX_ELIM = 3  # variables summed out by one launch (SBN_MAX_ELIM)
+MAX_Z = 256  # joint states of the variables summed out by one launch
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
@@ -101,12 +108,17 @@ class _Factor:
 @dataclass
 class Step:
     kind: int
-    inputs: list  # of (factor, sx, strides-per-out-axis)
-    out_slot: int
+    inputs: list  # of (factor, strides-per-eliminated-axis, strides-per-out-axis)
+    out_id: int  # logical id of the factor produced (slots are assigned afterwards)
     out_vars: tuple  # axis 0 (fastest) first
     cards: tuple
-    cx: int
-    elim: int | None
+    elims: tuple  # variables summed out by this launch
+    ecards: tuple
+    out_slot: int = -1
+
+    @property
+    def cx(self):
+        return int(np.prod(self.ecards, dtype=np.int64)) if self.ecards else 1
 
 
 @dataclass
@@ -223,7 +235,8 @@ def table_scale_log2(table: np.ndarray) -> int:
     return 0
 
 
-def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN) -> Plan:
+def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
+               merge_sum_outs=True) -> Plan:
     """Plan P(query | evidence) for `net`.
 
     query / evidence are sequences of var ids.  `evidence` fixes the evidence
@@ -272,27 +285,13 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         if set(order) != hidden or len(order) != len(hidden):
             raise ValueError("elimination order must be a permutation of the hidden variables")
 
-    slots = []  # physical: [batched, size, free?]
     steps = []
-
-    def alloc(batched, size):
-        best = None
-        for i, (b, s, free) in enumerate(slots):
-            if free and b == batched and s >= size and (best is None or s < slots[best][1]):
-                best = i
-        if best is None:
-            slots.append([batched, size, False])
-            return len(slots) - 1
-        slots[best][2] = False
-        return best
-
-    def release(f):
-        if f.is_slot:
-            slots[f.buf][2] = True
+    next_id = [0]
 
     def emit(inputs, elim, out_vars):
         """One fused launch: multiply `inputs`, sum out `elim` (None: product only).
-        out_vars is given fastest axis first."""
+        out_vars is given fastest axis first.  The output gets a logical id; physical
+        slots are assigned after the merge pass."""
         dep = any(f.depends_on_evidence for f in inputs)
         batched = dep and mode == MODE_BATCHED
         if len(out_vars) > MAX_AXES:
@@ -301,21 +300,21 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         size = int(np.prod(cards, dtype=np.int64)) if cards else 1
         if size >= 2**31:
             raise ValueError("a factor with >= 2^31 entries per row does not fit the 32-bit scope index")
-        out_slot = alloc(batched, size)
         ins = []
         for f in inputs:
             pos = {u: s for u, s in zip(f.vars, f.strides)}
-            ins.append((f, pos.get(elim, 0) if elim is not None else 0, tuple(pos.get(u, 0) for u in out_vars)))
-        steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_slot, tuple(out_vars), cards,
-                          int(card[elim]) if elim is not None else 1, elim))
-        for f in inputs:
-            release(f)
+            es = (pos.get(elim, 0),) if elim is not None else ()
+            ins.append((f, es, tuple(pos.get(u, 0) for u in out_vars)))
+        out_id = next_id[0]
+        next_id[0] += 1
+        steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_id, tuple(out_vars), cards,
+                          (elim,) if elim is not None else (), (int(card[elim]),) if elim is not None else ()))
         out_strides = []
         acc = 1
         for c in cards:
             out_strides.append(acc)
             acc *= c
-        return _Factor(True, out_slot, tuple(out_vars), tuple(out_strides), (), batched)
+        return _Factor(True, out_id, tuple(out_vars), tuple(out_strides), (), batched)
 
     def fsize(f):
         return int(np.prod([card[u] for u in f.vars], dtype=np.int64)) if f.vars else 1
@@ -379,12 +378,83 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     post = product_chain(factors, None, final_vars=tuple(reversed(q_sorted)))
     Q = fsize(post)
 
+    steps = _merge_sum_outs(steps, merge_sum_outs)
+    slots, post_slot = _assign_slots(steps, post.buf)
+
     plan = Plan(mode=mode, query=q_sorted, evidence=evidence, order=list(order), tables=tables,
                 table_scale_log2=[table_scale_log2(net.cpt[v]) for v in tables],
-                slots=[(bool(b), int(s)) for b, s, _ in slots], steps=steps, post_slot=post.buf, Q=Q)
+                slots=slots, steps=steps, post_slot=post_slot, Q=Q)
     plan._card = card
     _serialise(plan, net)
     return plan
+
+
+def _merge_sum_outs(steps, enabled=True):
+    """Fold a step whose ONLY input is the output of an earlier step into that step.
+
+    Such a step is a pure sum-out (or, with nothing to eliminate, a re-layout) of a factor
+    that was just produced: `sum_j (sum_x prod_i f_i)`.  Summing both variables in the
+    producer costs the same multiplies and saves writing the intermediate and reading it
+    back (25 KB of the 223 KB per query on the benchmark grid).  Every intermediate is
+    consumed exactly once, so the producer's original output is never needed."""
+    if not enabled:
+        return steps
+    merged = []
+    producer = {}  # logical id -> index into merged
+    for st in steps:
+        f0 = st.inputs[0][0]
+        if len(st.inputs) == 1 and f0.is_slot and not f0.ev and f0.buf in producer:
+            a = merged[producer[f0.buf]]
+            z = a.cx * st.cx
+            if a.kind == st.kind and len(a.elims) + len(st.elims) <= MAX_ELIM and z <= MAX_Z:
+                new_inputs = []
+                for f, es, _ in a.inputs:
+                    pos = {u: sd for u, sd in zip(f.vars, f.strides)}
+                    new_inputs.append((f, es + tuple(pos.get(y, 0) for y in st.elims),
+                                       tuple(pos.get(u, 0) for u in st.out_vars)))
+                a.inputs = new_inputs
+                a.elims = a.elims + st.elims
+                a.ecards = a.ecards + st.ecards
+                a.out_vars, a.cards = st.out_vars, st.cards
+                producer[st.out_id] = producer.pop(f0.buf)
+                a.out_id = st.out_id
+                continue
+        merged.append(st)
+        producer[st.out_id] = len(merged) - 1
+    return merged
+
+
+def _assign_slots(steps, post_id):
+    """Physical scratch slots by liveness: an output slot is taken before the step's inputs
+    are released (a launch never writes a buffer it reads), best fit among the free slots
+    of the same kind, and every intermediate dies with its single consumer."""
+    slots = []  # [batched, size, free]
+    where = {}  # logical id -> physical slot
+
+    def alloc(batched, size):
+        best = None
+        for i, (b, sz, free) in enumerate(slots):
+            if free and b == batched and sz >= size and (best is None or sz < slots[best][1]):
+                best = i
+        if best is None:
+            slots.append([batched, size, False])
+            return len(slots) - 1
+        slots[best][2] = False
+        return best
+
+    for st in steps:
+        size = int(np.prod(st.cards, dtype=np.int64)) if st.cards else 1
+        st.out_slot = alloc(st.kind == KIND_BATCHED, size)
+        new_inputs = []
+        for f, es, ss in st.inputs:
+            if f.is_slot:
+                phys = where.pop(f.buf)
+                slots[phys][2] = True
+                f = _Factor(True, phys, f.vars, f.strides, f.ev, f.batched)
+            new_inputs.append((f, es, ss))
+        st.inputs = new_inputs
+        where[st.out_id] = st.out_slot
+    return [(bool(b), int(sz)) for b, sz, _ in slots], where[post_id]
 
 
 def _serialise(plan: Plan, net: CompiledNet):
@@ -413,12 +483,14 @@ def _serialise(plan: Plan, net: CompiledNet):
     for b, s in plan.slots:
         w += [int(b), s]
     for st in plan.steps:
-        w += [st.kind, len(st.inputs), st.out_slot, len(st.cards), st.cx]
+        w += [st.kind, len(st.inputs), st.out_slot, len(st.cards), len(st.ecards)]
         w += list(st.cards)
-        for f, sx, strides in st.inputs:
-            w += [int(f.is_slot), f.buf, int(f.batched), sx, len(f.ev)]
+        w += list(st.ecards)
+        for f, estrides, strides in st.inputs:
+            w += [int(f.is_slot), f.buf, int(f.batched), len(f.ev)]
             for col, s, c in f.ev:
                 w += [col, s, c]
+            w += list(estrides)
             w += list(strides)
     arr = np.asarray(w, dtype=np.int64)
     if arr.max(initial=0) >= 2**31:

@@ -367,3 +367,34 @@ def test_graph_branches_match_linear_replay_and_plain_launches():
             prog.set_graph(mode)
             for _ in range(3):
                 assert np.array_equal(prog.run(codes, B), want), (wl.name, mode)
+
+
+def test_merged_sum_outs_match_unmerged_program_on_device():
+    """Launches that sum out several variables at once (joint-state offset tables) against
+    the one-variable-per-launch program, on the benchmark grid and a random DAG."""
+    from sorobn_b200 import BayesNet, engine, planner, synthetic, workloads
+
+    wl = workloads.grid10x10()
+    cases = [(wl.build(), wl.query, wl.evidence, None)]
+    spec = synthetic.random_dag(16, 3, (3, 4, 2), seed=77, window=6)
+    cases.append((synthetic.load(spec, BayesNet), (spec.nodes[-1],), tuple(spec.nodes[2:12:3]), spec))
+    for bn, query, evidence, spec in cases:
+        net = bn._compiled
+        q, e = [net.index[v] for v in query], [net.index[v] for v in evidence]
+        merged = planner.build_plan(net, q, e)
+        plain = planner.build_plan(net, q, e, merge_sum_outs=False)
+        B = 4099
+        if spec is None:
+            codes = wl.codes(bn, B, seed=8)
+        else:
+            ev = synthetic.random_events(spec, list(evidence), B, seed=8)
+            codes = np.stack([ev[v].to_numpy().astype(np.uint8) for v in evidence])
+        a = engine.Program(merged).run(codes, B)
+        b = engine.Program(plain).run(codes, B)
+        assert np.isfinite(a).all()
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-30)
+        # single-event float64 programs use the same merged plan
+        fm = planner.build_plan(net, q, e, mode=planner.MODE_FLAT)
+        fp = planner.build_plan(net, q, e, mode=planner.MODE_FLAT, merge_sum_outs=False)
+        one = np.ascontiguousarray(codes[:, :1])
+        assert np.allclose(engine.Program(fm, f64=True).run(one, 1), engine.Program(fp, f64=True).run(one, 1), rtol=1e-12)

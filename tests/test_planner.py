@@ -161,3 +161,46 @@ def test_tables_are_shipped_as_plain_probabilities():
     plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
     assert set(plan.table_scale_log2) == {0}
     assert plan.table_blob.max() <= 1.0 and plan.table_blob.min() >= 0.0
+
+
+def test_pure_sum_outs_are_folded_into_their_producer():
+    """`sum_out(*variables)` (bayes_net.py:54) takes several variables: an elimination whose only
+    factor is the product just built is folded into that launch.  Same answers, fewer bytes."""
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    q, e = [net.index[v] for v in wl.query], [net.index[v] for v in wl.evidence]
+    merged = planner.build_plan(net, q, e)
+    plain = planner.build_plan(net, q, e, merge_sum_outs=False)
+    assert len(merged.steps) < len(plain.steps)
+    assert merged.bytes_per_row() < 0.9 * plain.bytes_per_row()
+    assert merged.scratch_floats_per_row() <= plain.scratch_floats_per_row()
+    assert any(len(st.ecards) > 1 for st in merged.steps) and all(len(st.ecards) <= 1 for st in plain.steps)
+    assert all(len(st.ecards) <= planner.MAX_ELIM and st.cx <= planner.MAX_Z for st in merged.steps)
+    codes = wl.codes(bn, 5, seed=2)
+    a = program_interp.run(merged.words, merged.table_blob64, codes)
+    b = program_interp.run(plain.words, plain.table_blob64, codes)
+    assert np.allclose(a, b, rtol=1e-12, atol=0)
+    # no launch writes a slot it reads, also after the merge moved outputs around
+    for plan in (merged, plain):
+        for st in plan.steps:
+            assert all(not (f.is_slot and f.buf == st.out_slot) for f, _, _ in st.inputs)
+
+
+def test_chain_collapses_to_few_launches():
+    """A chain observed at the far end: every elimination after the first is a pure sum-out
+    of the previous product only when no new CPT joins, so nothing merges there; but a
+    query on the head with NO evidence eliminates the tail as re-layouts + sum-outs."""
+    spec = synthetic.chain(9, 4, seed=3)
+    bn = synthetic.load(spec, BayesNet)
+    net = bn._compiled
+    for q, ev in ((["c8"], []), (["c0"], ["c8"]), (["c4"], ["c0", "c8"])):
+        plan = planner.build_plan(net, [net.index[v] for v in q], [net.index[v] for v in ev], mode=planner.MODE_BATCHED)
+        ref = planner.build_plan(net, [net.index[v] for v in q], [net.index[v] for v in ev], mode=planner.MODE_BATCHED,
+                                 merge_sum_outs=False)
+        codes = np.zeros((len(ev), 3), dtype=np.uint8)
+        codes[:, 1] = 1
+        codes[:, 2] = 3
+        assert np.allclose(program_interp.run(plan.words, plan.table_blob64, codes, n_rows=3),
+                           program_interp.run(ref.words, ref.table_blob64, codes, n_rows=3), rtol=1e-12)
+        assert len(plan.steps) <= len(ref.steps)
