@@ -381,7 +381,7 @@ def test_merged_sum_outs_match_unmerged_program_on_device():
     for bn, query, evidence, spec in cases:
         net = bn._compiled
         q, e = [net.index[v] for v in query], [net.index[v] for v in evidence]
-        merged = planner.build_plan(net, q, e)
+        merged = planner.build_plan(net, q, e, merge_sum_outs=True)
         plain = planner.build_plan(net, q, e, merge_sum_outs=False)
         B = 4099
         if spec is None:
@@ -394,7 +394,7 @@ def test_merged_sum_outs_match_unmerged_program_on_device():
         assert np.isfinite(a).all()
         assert np.allclose(a, b, rtol=2e-6, atol=1e-30)
         # single-event float64 programs use the same merged plan
-        fm = planner.build_plan(net, q, e, mode=planner.MODE_FLAT)
+        fm = planner.build_plan(net, q, e, mode=planner.MODE_FLAT, merge_sum_outs=True)
         fp = planner.build_plan(net, q, e, mode=planner.MODE_FLAT, merge_sum_outs=False)
         one = np.ascontiguousarray(codes[:, :1])
         assert np.allclose(engine.Program(fm, f64=True).run(one, 1), engine.Program(fp, f64=True).run(one, 1), rtol=1e-12)

@@ -170,7 +170,7 @@ def test_pure_sum_outs_are_folded_into_their_producer():
     bn = wl.build()
     net = bn._compiled
     q, e = [net.index[v] for v in wl.query], [net.index[v] for v in wl.evidence]
-    merged = planner.build_plan(net, q, e)
+    merged = planner.build_plan(net, q, e, merge_sum_outs=True)
     plain = planner.build_plan(net, q, e, merge_sum_outs=False)
     assert len(merged.steps) < len(plain.steps)
     assert merged.bytes_per_row() < 0.9 * plain.bytes_per_row()
@@ -195,7 +195,8 @@ def test_chain_collapses_to_few_launches():
     bn = synthetic.load(spec, BayesNet)
     net = bn._compiled
     for q, ev in ((["c8"], []), (["c0"], ["c8"]), (["c4"], ["c0", "c8"])):
-        plan = planner.build_plan(net, [net.index[v] for v in q], [net.index[v] for v in ev], mode=planner.MODE_BATCHED)
+        plan = planner.build_plan(net, [net.index[v] for v in q], [net.index[v] for v in ev], mode=planner.MODE_BATCHED,
+                                  merge_sum_outs=True)
         ref = planner.build_plan(net, [net.index[v] for v in q], [net.index[v] for v in ev], mode=planner.MODE_BATCHED,
                                  merge_sum_outs=False)
         codes = np.zeros((len(ev), 3), dtype=np.uint8)
