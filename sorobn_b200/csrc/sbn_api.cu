@@ -67,7 +67,7 @@ struct StepDesc {
     std::vector<InDesc> in;
     // tiled fast path (sbn_step_tiled): tile edge, tile count, offset-table position
     int tile = 0;            // 0 = not eligible, use sbn_step_batched
-    int nu = 0, na = 0, nb = 0;  // inputs without a tile axis / with axis 0 / with axis 1
+    int nu = 0, na = 0, nb = 0, nc = 0;  // inputs without a tile axis / with axis 0 / axis 1 / both
     std::vector<int> order;      // kernel input slot -> index into `in` (U, then A, then B)
     int64_t n_tiles = 0;
     int64_t tile_off_pos = 0;  // int32 offset into sbn_program::d_tile_off
@@ -287,7 +287,7 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
     for (StepDesc &st : P->steps) {
         st.tile = 0;
         if (st.kind != 1 || st.in.size() > static_cast<size_t>(kTiledMaxIn)) continue;
-        if (st.ecards.size() > 1) continue;  // several eliminated axes: plain kernel
+
         int64_t smem = 0;
         for (const InDesc &in : st.in)
             if (!in.batched) smem += in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
@@ -297,32 +297,38 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         const int c1 = n_axes > 1 ? st.cards[1] : 1;
         if (c0 > 255 * 5 || c1 > 255 * 5) continue;
         // sort the inputs by the tile axes they carry
-        std::vector<int> us, as, bs;
-        bool both = false;
+        std::vector<int> us, as, bs, cs;
         for (size_t i = 0; i < st.in.size(); ++i) {
             const bool h0 = n_axes > 0 && st.in[i].strides[0] != 0;
             const bool h1 = n_axes > 1 && st.in[i].strides[1] != 0;
-            if (h0 && h1) both = true;
+            if (h0 && h1) cs.push_back(static_cast<int>(i));
             else if (h0) as.push_back(static_cast<int>(i));
             else if (h1) bs.push_back(static_cast<int>(i));
             else us.push_back(static_cast<int>(i));
         }
-        if (both) continue;  // an input spans the whole tile: sbn_step_batched streams it
-        // a factor without tile axes may ride on either side (stride 0 re-reads one entry)
-        while (us.size() > 2 || (as.empty() && !us.empty())) {
-            if (as.size() < 2) as.push_back(us.back());
-            else if (n_axes > 1 && bs.size() < 2) bs.push_back(us.back());
-            else break;
-            us.pop_back();
+        if (cs.size() > 1) continue;  // two inputs span the whole tile: plain kernel
+        if (cs.empty()) {
+            // a factor without tile axes may ride on either side (stride 0 re-reads one entry)
+            while (us.size() > 2 || (as.empty() && !us.empty())) {
+                if (as.size() < 2) as.push_back(us.back());
+                else if (n_axes > 1 && bs.size() < 2) bs.push_back(us.back());
+                else break;
+                us.pop_back();
+            }
+            if (us.size() > 2 || as.empty() || as.size() > 2 || bs.size() > 2) continue;
+            if (n_axes > 1 && bs.empty()) continue;
+        } else {
+            // with a C-side input the instantiated combinations are NU, NA, NB <= 1
+            if (us.size() > 1 || as.size() > 1 || bs.size() > 1) continue;
         }
-        if (us.size() > 2 || as.empty() || as.size() > 2 || bs.size() > 2) continue;
-        if (n_axes > 1 && bs.empty()) continue;
         st.nu = static_cast<int>(us.size());
         st.na = static_cast<int>(as.size());
         st.nb = static_cast<int>(bs.size());
+        st.nc = static_cast<int>(cs.size());
         st.order = us;
         st.order.insert(st.order.end(), as.begin(), as.end());
         st.order.insert(st.order.end(), bs.begin(), bs.end());
+        st.order.insert(st.order.end(), cs.begin(), cs.end());
         // tile edge: least padding waste, ties to the larger tile
         int best_t = 2;
         double best_w = 1e30;
@@ -518,66 +524,87 @@ cudaError_t set_smem_attr_n() {
     return e;
 }
 
-// (NU, NA, NB) combinations instantiated: NU <= 2, 1 <= NA <= 2, NB <= 2, at most 4 inputs
-#define SBN_TILED_COMBOS(X) \
-    X(0, 1, 0) X(0, 1, 1) X(0, 1, 2) X(0, 2, 0) X(0, 2, 1) X(0, 2, 2) X(1, 1, 0) X(1, 1, 1) X(1, 1, 2) \
-    X(1, 2, 0) X(1, 2, 1) X(2, 1, 0) X(2, 1, 1) X(2, 2, 0)
+// (NU, NA, NB, NC) combinations instantiated.  Without a C-side input: NU <= 2, 1 <= NA <= 2,
+// NB <= 2, at most 4 inputs.  With one: NU, NA, NB <= 1.
+#define SBN_TILED_COMBOS(X)                                                                          \
+    X(0, 1, 0, 0) X(0, 1, 1, 0) X(0, 1, 2, 0) X(0, 2, 0, 0) X(0, 2, 1, 0) X(0, 2, 2, 0) X(1, 1, 0, 0)   \
+    X(1, 1, 1, 0) X(1, 1, 2, 0) X(1, 2, 0, 0) X(1, 2, 1, 0) X(2, 1, 0, 0) X(2, 1, 1, 0) X(2, 2, 0, 0)
+#define SBN_TILED_COMBOS_C(X)                                                                        \
+    X(0, 0, 0, 1) X(0, 0, 1, 1) X(0, 1, 0, 1) X(0, 1, 1, 1) X(1, 0, 0, 1) X(1, 0, 1, 1) X(1, 1, 0, 1)   \
+    X(1, 1, 1, 1)
 
 constexpr int kV = kRowsPerThread;  // evidence rows per thread of the tiled kernel
 
 // Preload variants (CX > 0) exist where the tile edge equals the eliminated cardinality
-// (networks with one cardinality throughout: 2, 3, 4, 5 states) and for 8 states (T = 4).
-template <int NU, int NA, int NB>
+// (networks with one cardinality throughout: 2, 3, 4, 5 states) and for 8 states (T = 4);
+// never with a C-side input or several eliminated variables.
+template <int NU, int NA, int NB, int NC>
 cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t grid, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
     const dim3 g(static_cast<unsigned>(grid)), b(SBN_TILED_THREADS);
-#define SBN_T(TV)                                                                      \
-    case TV:                                                                           \
-        if (preload && q.cx == TV) sbn_step_tiled<NU, NA, NB, TV, kV, TV><<<g, b, smem, stream>>>(q); \
-        else sbn_step_tiled<NU, NA, NB, TV, kV, 0><<<g, b, smem, stream>>>(q);         \
+    if constexpr (NC > 0) {
+        switch (tile) {
+            case 2: sbn_step_tiled<NU, NA, NB, NC, 2, kV, 0><<<g, b, smem, stream>>>(q); break;
+            case 3: sbn_step_tiled<NU, NA, NB, NC, 3, kV, 0><<<g, b, smem, stream>>>(q); break;
+            case 4: sbn_step_tiled<NU, NA, NB, NC, 4, kV, 0><<<g, b, smem, stream>>>(q); break;
+            case 5: sbn_step_tiled<NU, NA, NB, NC, 5, kV, 0><<<g, b, smem, stream>>>(q); break;
+            default: return cudaErrorInvalidValue;
+        }
+    } else {
+#define SBN_T(TV)                                                                            \
+    case TV:                                                                                 \
+        if (preload && q.cx == TV) sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV><<<g, b, smem, stream>>>(q); \
+        else sbn_step_tiled<NU, NA, NB, 0, TV, kV, 0><<<g, b, smem, stream>>>(q);            \
         break;
-    switch (tile) {
-        SBN_T(2)
-        SBN_T(3)
-        SBN_T(5)
-        case 4:
-            if (preload && q.cx == 4) sbn_step_tiled<NU, NA, NB, 4, kV, 4><<<g, b, smem, stream>>>(q);
-            else if (preload && q.cx == 8) sbn_step_tiled<NU, NA, NB, 4, kV, 8><<<g, b, smem, stream>>>(q);
-            else sbn_step_tiled<NU, NA, NB, 4, kV, 0><<<g, b, smem, stream>>>(q);
-            break;
-        default: return cudaErrorInvalidValue;
-    }
+        switch (tile) {
+            SBN_T(2)
+            SBN_T(3)
+            SBN_T(5)
+            case 4:
+                if (preload && q.cx == 4) sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4><<<g, b, smem, stream>>>(q);
+                else if (preload && q.cx == 8) sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8><<<g, b, smem, stream>>>(q);
+                else sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0><<<g, b, smem, stream>>>(q);
+                break;
+            default: return cudaErrorInvalidValue;
+        }
 #undef SBN_T
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int64_t grid, cudaStream_t stream) {
-    const int key = st.nu * 100 + st.na * 10 + st.nb;
-    // the preload schedule keeps every operand of a tile in registers: only for <= 3 inputs
-    preload = preload && st.in.size() <= 3;
+    const int key = st.nu * 1000 + st.na * 100 + st.nb * 10 + st.nc;
+    // the preload schedule keeps every operand of a tile in registers: only for <= 3 inputs,
+    // one eliminated variable
+    preload = preload && st.in.size() <= 3 && q.zoff == nullptr;
     switch (key) {
-#define X(U, A, B) \
-    case U * 100 + A * 10 + B: return launch_tiled_c<U, A, B>(q, st.tile, preload, grid, stream);
+#define X(U, A, B, C) \
+    case U * 1000 + A * 100 + B * 10 + C: return launch_tiled_c<U, A, B, C>(q, st.tile, preload, grid, stream);
         SBN_TILED_COMBOS(X)
+        SBN_TILED_COMBOS_C(X)
 #undef X
     }
     return cudaErrorInvalidValue;
 }
 
-template <int NU, int NA, int NB>
+template <int NU, int NA, int NB, int NC>
 cudaError_t set_tiled_attr_c() {
     cudaError_t e = cudaSuccess;
 #define SBN_A(TV, CXV) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
-    SBN_A(2, 0) SBN_A(2, 2) SBN_A(3, 0) SBN_A(3, 3) SBN_A(4, 0) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 0) SBN_A(5, 5)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    SBN_A(2, 0) SBN_A(3, 0) SBN_A(4, 0) SBN_A(5, 0)
+    if constexpr (NC == 0) {
+        SBN_A(2, 2) SBN_A(3, 3) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 5)
+    }
 #undef SBN_A
     return e;
 }
 cudaError_t set_tiled_attrs() {
     cudaError_t e = cudaSuccess;
-#define X(U, A, B) \
-    if (e == cudaSuccess) e = set_tiled_attr_c<U, A, B>();
+#define X(U, A, B, C) \
+    if (e == cudaSuccess) e = set_tiled_attr_c<U, A, B, C>();
     SBN_TILED_COMBOS(X)
+    SBN_TILED_COMBOS_C(X)
 #undef X
     return e;
 }

@@ -278,20 +278,28 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 #define SBN_TILED_THREADS 128
 
 // Inputs arrive sorted by the host: NU that carry neither tile axis, then NA that carry
-// axis 0 only, then NB that carry axis 1 only (an input with both axes sends the step to
-// sbn_step_batched instead).  Per eliminated state x:
+// axis 0 only, then NB that carry axis 1 only, then NC (0 or 1) that carries both.  Per
+// eliminated state x:
 //     a[d0] = prod_U in(x) * prod_A in(x, d0)      T values
 //     b[d1] = prod_B in(x, d1)                     T values
-//     acc[d0][d1] += a[d0] * b[d1]                 T*T FFMA
+//     acc[d0][d1] += a[d0] * b[d1] (* c(x, d0, d1))  T*T FFMA
+// An input on the C side is read once per output and per x -- each of its entries exactly
+// once overall: that is the streaming operand of a sum-out.
 //
 // CX > 0 (compile-time number of eliminated states) selects the *preload* schedule: every
 // operand of the tile, for all x, is fetched into registers before the first FFMA, so a
 // thread keeps CX * (NA * T + NB * T + NU) loads in flight instead of one x-step's worth
 // (the kernel is latency-bound otherwise: ~16 warps per SM because of the accumulators).
-template <int NU, int NA, int NB, int T, int V, int CX>
-__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_tiled(const __grid_constant__ SbnStep p) {
-    constexpr int N_IN = NU + NA + NB;
-    constexpr int TB = NB > 0 ? T : 1;  // no B-side input: the output has a single axis
+// With a C-side input (T*T loads per x already) only the x-loop schedule is built.
+// When several variables are eliminated at once, x runs over their joint states and the
+// per-input element offset comes from `zoff` instead of x * sx.
+template <int NU, int NA, int NB, int NC, int T, int V, int CX>
+__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 : 4)))
+    sbn_step_tiled(const __grid_constant__ SbnStep p) {
+    constexpr int N_IN = NU + NA + NB + NC;
+    constexpr int TB = (NB > 0 || NC > 0) ? T : 1;  // no input with axis 1: single-axis output
+    static_assert(NC <= 1, "one input may span both tile axes");
+    static_assert(CX == 0 || NC == 0, "the preload schedule does not cover a C-side input");
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -350,6 +358,19 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
     const int t_begin = chunk * p.tiles_per_cta;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
     float *const outp = p.out + b;
+    const int cx = p.cx;
+
+    // element offset of eliminated state x in input i
+    auto xoff = [&](int i, int x) { return p.zoff ? __ldg(p.zoff + i * cx + x) : x * p.in[i].sx; };
+    // V rows of input i at element offset e
+    auto fetch = [&](int i, int e, float (&r)[V]) {
+        if (p.in[i].batched) {
+            sbn_ldv<V>(r, gsrc[i] + static_cast<int64_t>(e) * ld);
+        } else {
+#pragma unroll
+            for (int l = 0; l < V; ++l) r[l] = s_tab[evo[i][l] + e];
+        }
+    };
 
     for (int t = t_begin; t < t_end; ++t) {
         const int32_t *row = p.tile_off + static_cast<int64_t>(t) * (N_IN + 2);
@@ -380,57 +401,30 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
 
             if constexpr (CX > 0) {
                 // ---- preload schedule: all loads first ...
-                float ra[NA][CX][T][V], rb[NB > 0 ? NB : 1][CX][TB][V], ru[NU > 0 ? NU : 1][CX][V];
+                float ra[NA > 0 ? NA : 1][CX][T][V], rb[NB > 0 ? NB : 1][CX][TB][V], ru[NU > 0 ? NU : 1][CX][V];
 #pragma unroll
                 for (int j = 0; j < NA; ++j) {
                     const int i = NU + j;
                     const int s0 = p.in[i].stride[0], sx = p.in[i].sx;
-                    if (p.in[i].batched) {
 #pragma unroll
-                        for (int x = 0; x < CX; ++x)
+                    for (int x = 0; x < CX; ++x)
 #pragma unroll
-                            for (int d = 0; d < T; ++d)
-                                sbn_ldv<V>(ra[j][x][d], gsrc[i] + static_cast<int64_t>(base[i] + x * sx + k0[d] * s0) * ld);
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < CX; ++x)
-#pragma unroll
-                            for (int d = 0; d < T; ++d)
-#pragma unroll
-                                for (int l = 0; l < V; ++l) ra[j][x][d][l] = s_tab[evo[i][l] + base[i] + x * sx + k0[d] * s0];
-                    }
+                        for (int d = 0; d < T; ++d) fetch(i, base[i] + x * sx + k0[d] * s0, ra[j][x][d]);
                 }
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     const int i = NU + NA + j;
                     const int s1 = p.in[i].stride[1], sx = p.in[i].sx;
-                    if (p.in[i].batched) {
 #pragma unroll
-                        for (int x = 0; x < CX; ++x)
+                    for (int x = 0; x < CX; ++x)
 #pragma unroll
-                            for (int d = 0; d < TB; ++d)
-                                sbn_ldv<V>(rb[j][x][d], gsrc[i] + static_cast<int64_t>(base[i] + x * sx + k1[d] * s1) * ld);
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < CX; ++x)
-#pragma unroll
-                            for (int d = 0; d < TB; ++d)
-#pragma unroll
-                                for (int l = 0; l < V; ++l) rb[j][x][d][l] = s_tab[evo[i][l] + base[i] + x * sx + k1[d] * s1];
-                    }
+                        for (int d = 0; d < TB; ++d) fetch(i, base[i] + x * sx + k1[d] * s1, rb[j][x][d]);
                 }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
                     const int sx = p.in[i].sx;
-                    if (p.in[i].batched) {
 #pragma unroll
-                        for (int x = 0; x < CX; ++x) sbn_ldv<V>(ru[i][x], gsrc[i] + static_cast<int64_t>(base[i] + x * sx) * ld);
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < CX; ++x)
-#pragma unroll
-                            for (int l = 0; l < V; ++l) ru[i][x][l] = s_tab[evo[i][l] + base[i] + x * sx];
-                    }
+                    for (int x = 0; x < CX; ++x) fetch(i, base[i] + x * sx, ru[i][x]);
                 }
                 // ---- ... then the arithmetic
 #pragma unroll
@@ -440,9 +434,9 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
                     for (int d = 0; d < T; ++d)
 #pragma unroll
                         for (int l = 0; l < V; ++l) {
-                            float v = ra[0][x][d][l];
+                            float v = 1.f;
 #pragma unroll
-                            for (int j = 1; j < NA; ++j) v *= ra[j][x][d][l];
+                            for (int j = 0; j < NA; ++j) v = (j == 0) ? ra[j][x][d][l] : v * ra[j][x][d][l];
 #pragma unroll
                             for (int i = 0; i < NU; ++i) v *= ru[i][x][l];
                             a[d][l] = v;
@@ -452,11 +446,8 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
 #pragma unroll
                         for (int l = 0; l < V; ++l) {
                             float v = 1.f;
-                            if constexpr (NB > 0) {
-                                v = rb[0][x][d][l];
 #pragma unroll
-                                for (int j = 1; j < NB; ++j) v *= rb[j][x][d][l];
-                            }
+                            for (int j = 0; j < NB; ++j) v = (j == 0) ? rb[j][x][d][l] : v * rb[j][x][d][l];
                             bb[d][l] = v;
                         }
 #pragma unroll
@@ -468,78 +459,78 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : 4)) sbn_step_
                 }
             } else {
 #pragma unroll 2
-            for (int x = 0; x < p.cx; ++x) {
-                float a[T][V], bb[TB][V];
-                // ---- A side (first A input initialises, the others multiply in)
-#pragma unroll
-                for (int j = 0; j < NA; ++j) {
-                    const int i = NU + j;
-                    const int e = base[i] + x * p.in[i].sx;
-                    const int s0 = p.in[i].stride[0];
-                    float r[T][V];
-                    if (p.in[i].batched) {
-#pragma unroll
-                        for (int d = 0; d < T; ++d) sbn_ldv<V>(r[d], gsrc[i] + static_cast<int64_t>(e + k0[d] * s0) * ld);
-                    } else {
-#pragma unroll
-                        for (int d = 0; d < T; ++d)
-#pragma unroll
-                            for (int l = 0; l < V; ++l) r[d][l] = s_tab[evo[i][l] + e + k0[d] * s0];
-                    }
+                for (int x = 0; x < cx; ++x) {
+                    float a[T][V], bb[TB][V];
 #pragma unroll
                     for (int d = 0; d < T; ++d)
 #pragma unroll
-                        for (int l = 0; l < V; ++l) a[d][l] = (j == 0) ? r[d][l] : a[d][l] * r[d][l];
-                }
-                // ---- U side folds into a[]
-#pragma unroll
-                for (int i = 0; i < NU; ++i) {
-                    const int e = base[i] + x * p.in[i].sx;
-                    float r[V];
-                    if (p.in[i].batched) {
-                        sbn_ldv<V>(r, gsrc[i] + static_cast<int64_t>(e) * ld);
-                    } else {
-#pragma unroll
-                        for (int l = 0; l < V; ++l) r[l] = s_tab[evo[i][l] + e];
-                    }
-#pragma unroll
-                    for (int d = 0; d < T; ++d)
-#pragma unroll
-                        for (int l = 0; l < V; ++l) a[d][l] *= r[l];
-                }
-                // ---- B side
-                if constexpr (NB == 0) {
-#pragma unroll
-                    for (int l = 0; l < V; ++l) bb[0][l] = 1.f;
-                }
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int i = NU + NA + j;
-                    const int e = base[i] + x * p.in[i].sx;
-                    const int s1 = p.in[i].stride[1];
-                    float r[TB][V];
-                    if (p.in[i].batched) {
-#pragma unroll
-                        for (int d = 0; d < TB; ++d) sbn_ldv<V>(r[d], gsrc[i] + static_cast<int64_t>(e + k1[d] * s1) * ld);
-                    } else {
-#pragma unroll
-                        for (int d = 0; d < TB; ++d)
-#pragma unroll
-                            for (int l = 0; l < V; ++l) r[d][l] = s_tab[evo[i][l] + e + k1[d] * s1];
-                    }
+                        for (int l = 0; l < V; ++l) a[d][l] = 1.f;
 #pragma unroll
                     for (int d = 0; d < TB; ++d)
 #pragma unroll
-                        for (int l = 0; l < V; ++l) bb[d][l] = (j == 0) ? r[d][l] : bb[d][l] * r[d][l];
+                        for (int l = 0; l < V; ++l) bb[d][l] = 1.f;
+                    // ---- C side first: the largest batch of independent loads
+                    float rc[NC > 0 ? T : 1][NC > 0 ? TB : 1][V];
+                    if constexpr (NC > 0) {
+                        constexpr int i = NU + NA + NB;
+                        const int e = base[i] + xoff(i, x);
+                        const int s0 = p.in[i].stride[0], s1 = p.in[i].stride[1];
+#pragma unroll
+                        for (int d0 = 0; d0 < T; ++d0)
+#pragma unroll
+                            for (int d1 = 0; d1 < TB; ++d1) fetch(i, e + k0[d0] * s0 + k1[d1] * s1, rc[d0][d1]);
+                    }
+                    // ---- A side
+#pragma unroll
+                    for (int j = 0; j < NA; ++j) {
+                        const int i = NU + j;
+                        const int e = base[i] + xoff(i, x);
+                        const int s0 = p.in[i].stride[0];
+                        float r[T][V];
+#pragma unroll
+                        for (int d = 0; d < T; ++d) fetch(i, e + k0[d] * s0, r[d]);
+#pragma unroll
+                        for (int d = 0; d < T; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) a[d][l] *= r[d][l];
+                    }
+                    // ---- U side folds into a[]
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        float r[V];
+                        fetch(i, base[i] + xoff(i, x), r);
+#pragma unroll
+                        for (int d = 0; d < T; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) a[d][l] *= r[l];
+                    }
+                    // ---- B side
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int i = NU + NA + j;
+                        const int e = base[i] + xoff(i, x);
+                        const int s1 = p.in[i].stride[1];
+                        float r[TB][V];
+#pragma unroll
+                        for (int d = 0; d < TB; ++d) fetch(i, e + k1[d] * s1, r[d]);
+#pragma unroll
+                        for (int d = 0; d < TB; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) bb[d][l] *= r[d][l];
+                    }
+                    // ---- outer product into the accumulators
+#pragma unroll
+                    for (int d0 = 0; d0 < T; ++d0)
+#pragma unroll
+                        for (int d1 = 0; d1 < TB; ++d1)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) {
+                                if constexpr (NC > 0)
+                                    acc[d0][d1][l] = fmaf(a[d0][l] * bb[d1][l], rc[d0][d1][l], acc[d0][d1][l]);
+                                else
+                                    acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                            }
                 }
-                // ---- outer product into the accumulators
-#pragma unroll
-                for (int d0 = 0; d0 < T; ++d0)
-#pragma unroll
-                    for (int d1 = 0; d1 < TB; ++d1)
-#pragma unroll
-                        for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
-            }
             }
 #pragma unroll
             for (int d1 = 0; d1 < TB; ++d1)

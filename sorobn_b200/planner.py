@@ -47,6 +47,7 @@ input that spans both tile axes.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -240,12 +241,14 @@ def table_scale_log2(table: np.ndarray) -> int:
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
-               merge_sum_outs=False) -> Plan:
+               merge_sum_outs=None) -> Plan:
     """Plan P(query | evidence) for `net`.
 
     query / evidence are sequences of var ids.  `evidence` fixes the evidence
     *columns*; their values arrive at run time.
     """
+    if merge_sum_outs is None:
+        merge_sum_outs = os.environ.get("SOROBN_B200_MERGE", "0") == "1"
     query = tuple(query)
     evidence = tuple(evidence)
     if not query:
