@@ -275,12 +275,20 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     # per-row gathers instead of boolean filters
     tables = sorted(relevant)
     factors = []
+    table_arrays = []
     for t, v in enumerate(tables):
         scope = net.scope(v)
-        shape = [int(card[u]) for u in scope]
+        # Shipped layout: free axes first (reference order), evidence axes innermost.  Rows of
+        # a warp differ only in their evidence codes, so their gathers of one entry then fall
+        # into one 32-byte sector / distinct shared-memory banks instead of `stride` apart.
+        perm = [i for i, u in enumerate(scope) if u not in ev_col] + [i for i, u in enumerate(scope) if u in ev_col]
+        arr = np.ascontiguousarray(np.transpose(net.cpt[v], perm))
+        table_arrays.append(arr)
+        pscope = [scope[i] for i in perm]
+        shape = [int(card[u]) for u in pscope]
         strides = [int(np.prod(shape[i + 1:], dtype=np.int64)) for i in range(len(shape))]
-        free = [(u, s) for u, s in zip(scope, strides) if u not in ev_col]
-        ev = tuple((ev_col[u], s, int(card[u])) for u, s in zip(scope, strides) if u in ev_col)
+        free = [(u, s) for u, s in zip(pscope, strides) if u not in ev_col]
+        ev = tuple((ev_col[u], s, int(card[u])) for u, s in zip(pscope, strides) if u in ev_col)
         if len(ev) > MAX_EV:
             raise ValueError(f"CPT of {net.names[v]!r} has {len(ev)} evidence axes; the kernel supports {MAX_EV}")
         factors.append(_Factor(False, t, tuple(u for u, _ in free), tuple(s for _, s in free), ev, False))
@@ -392,7 +400,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
                 table_scale_log2=[table_scale_log2(net.cpt[v]) for v in tables],
                 slots=slots, steps=steps, post_slot=post_slot, Q=Q)
     plan._card = card
-    _serialise(plan, net)
+    _serialise(plan, table_arrays)
     return plan
 
 
@@ -464,12 +472,12 @@ def _assign_slots(steps, post_id):
     return [(bool(b), int(sz)) for b, sz, _ in slots], where[post_id]
 
 
-def _serialise(plan: Plan, net: CompiledNet):
+def _serialise(plan: Plan, table_arrays):
     blob = []
     offsets = []
     off = 0
-    for v, k in zip(plan.tables, plan.table_scale_log2):
-        t = np.ldexp(net.cpt[v].astype(np.float64), k).reshape(-1)
+    for arr, k in zip(table_arrays, plan.table_scale_log2):
+        t = np.ldexp(arr.astype(np.float64), k).reshape(-1)
         pad = (-t.size) % 4  # keep every table 16-byte aligned and sized (bulk-TMA copies)
         offsets.append((off, t.size))
         blob.append(t)
