@@ -334,7 +334,8 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         double best_w = 1e30;
         for (int t = 2; t <= 5; ++t) {
             auto waste = [&](int c) { return static_cast<double>((c + t - 1) / t * t) / c; };
-            const double w = waste(c0) * waste(c1);
+            // a single-axis output has a T x 1 tile: axis 1 wastes nothing
+            const double w = waste(c0) * (n_axes > 1 ? waste(c1) : 1.0);
             if (w < best_w - 1e-9 || (w < best_w + 1e-9 && t > best_t)) {
                 best_w = w;
                 best_t = t;
