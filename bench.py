@@ -56,16 +56,21 @@ def parse_args():
 
 # ------------------------------------------------------------------ clocks sampling
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU through NVML every ~2 ms while the
-    timed region runs (the CLI nvidia-smi is too slow for a 50 ms region)."""
+    """Samples SM clock and throttle reasons of one GPU through NVML every ~2 ms.  The thread
+    is started early (NVML init takes longer than the timed region); `begin()` / `end()`
+    bracket the timed region and only samples taken in between are reported."""
 
     def __init__(self, index: int):
         self.index = index
         self.sm, self.reasons_seen = [], 0
         self.max_sm = None
         self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._ready = threading.Event()
+        self._active = False
         self._ok = False
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        self._ready.wait(timeout=20)
 
     def _run(self):
         try:
@@ -75,21 +80,27 @@ class ClockSampler:
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             self._ok = True
+            self._ready.set()
             while not self._stop.is_set():
-                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                try:
-                    self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                if self._active:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    try:
+                        self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        self.reasons_seen |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 self._stop.wait(0.002)
         except Exception:
             self._ok = False
+            self._ready.set()
 
-    def __enter__(self):
-        self._thread.start()
-        return self
+    def begin(self):
+        self.sm, self.reasons_seen = [], 0
+        self._active = True
 
-    def __exit__(self, *exc):
+    def end(self):
+        self._active = False
+
+    def close(self):
         self._stop.set()
         self._thread.join(timeout=6)
 
@@ -246,12 +257,14 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
     for _ in range(args.warmup):
         device_step()
     barrier()
     launches0 = prog.info()["launches"]
 
-    with ClockSampler(local_rank) as clocks:
+    clocks.begin()
+    if True:
         if flush is None:
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -283,7 +296,9 @@ def run_b200(args, rank, world, local_rank):
             prog.run(codes_host.array[:n_ev], rows, out=out_host.array)
         barrier()
         e2e_s = time.perf_counter() - t0
+    clocks.end()
     clock_summary = clocks.summary()
+    clocks.close()
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if distributed:
