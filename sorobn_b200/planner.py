@@ -60,6 +60,7 @@ MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
 TILE_EDGE = 5  # largest register-tile edge of sbn_step_tiled
 MAX_ELIM = 3  # variables summed out by one launch (SBN_MAX_ELIM)
 MAX_Z = 256  # joint states of the variables summed out by one launch
+LIFT_MAX = 16384  # entries of a table that keeps evidence axes (64 KB: still staged in shared memory)
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
@@ -102,7 +103,7 @@ class _Factor:
     buf: int  # table index or slot index
     vars: tuple  # free variable ids
     strides: tuple  # element stride per free variable
-    ev: tuple  # ((ev_col, stride, card), ...) -- only raw tables carry these
+    ev: tuple  # ((ev_col, stride, card), ...) -- CPTs and tables that kept evidence axes (never batched)
     batched: bool
 
     @property
@@ -241,7 +242,7 @@ def table_scale_log2(table: np.ndarray) -> int:
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
-               merge_sum_outs=None) -> Plan:
+               merge_sum_outs=None, lift_evidence=True) -> Plan:
     """Plan P(query | evidence) for `net`.
 
     query / evidence are sequences of var ids.  `evidence` fixes the evidence
@@ -303,10 +304,18 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     steps = []
     next_id = [0]
 
-    def emit(inputs, elim, out_vars):
+    def emit(inputs, elim, out_vars, may_lift=True):
         """One fused launch: multiply `inputs`, sum out `elim` (None: product only).
         out_vars is given fastest axis first.  The output gets a logical id; physical
-        slots are assigned after the merge pass."""
+        slots are assigned after the merge pass.
+
+        Deferred evidence instantiation: when every input is a table (CPTs, or tables built
+        this way), the product depends on the evidence row only through the few evidence
+        columns those tables are indexed by.  It is then computed ONCE, as a table that keeps
+        those evidence variables as ordinary (innermost) axes, by an evidence-independent flat
+        launch; consumers gather from it like from a CPT.  The reference filters every CPT by
+        the event first (bayes_net.py:772-774); filtering after multiplying gives the same
+        numbers and turns per-row work into per-call work."""
         dep = any(f.depends_on_evidence for f in inputs)
         batched = dep and mode == MODE_BATCHED
         if len(out_vars) > MAX_AXES:
@@ -315,13 +324,45 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         size = int(np.prod(cards, dtype=np.int64)) if cards else 1
         if size >= 2**31:
             raise ValueError("a factor with >= 2^31 entries per row does not fit the 32-bit scope index")
+
+        lifted_cols = None
+        if batched and lift_evidence and may_lift and not any(f.batched for f in inputs):
+            cols = []
+            for f in inputs:
+                for col, _, c in f.ev:
+                    if (col, c) not in cols:
+                        cols.append((col, c))
+            lifted = size * int(np.prod([c for _, c in cols], dtype=np.int64))
+            if len(cols) <= MAX_EV and lifted <= LIFT_MAX and len(out_vars) + len(cols) <= MAX_AXES:
+                lifted_cols = cols
+
         ins = []
+        out_id = next_id[0]
+        next_id[0] += 1
+        if lifted_cols is not None:
+            ev_vars = [evidence[col] for col, _ in lifted_cols]
+            axes = tuple(ev_vars) + tuple(out_vars)  # evidence axes innermost
+            axis_cards = tuple(c for _, c in lifted_cols) + cards
+            for f in inputs:
+                pos = {u: sd for u, sd in zip(f.vars, f.strides)}
+                pos.update({evidence[col]: sd for col, sd, _ in f.ev})
+                es = (pos.get(elim, 0),) if elim is not None else ()
+                plain = _Factor(f.is_slot, f.buf, f.vars, f.strides, (), False)  # evidence axes are output axes here
+                ins.append((plain, es, tuple(pos.get(u, 0) for u in axes)))
+            steps.append(Step(KIND_FLAT, ins, out_id, axes, axis_cards,
+                              (elim,) if elim is not None else (), (int(card[elim]),) if elim is not None else ()))
+            strides, acc = [], 1
+            for c in axis_cards:
+                strides.append(acc)
+                acc *= c
+            n_ev = len(lifted_cols)
+            ev = tuple((col, strides[k], c) for k, (col, c) in enumerate(lifted_cols))
+            return _Factor(True, out_id, tuple(out_vars), tuple(strides[n_ev:]), ev, False)
+
         for f in inputs:
             pos = {u: s for u, s in zip(f.vars, f.strides)}
             es = (pos.get(elim, 0),) if elim is not None else ()
             ins.append((f, es, tuple(pos.get(u, 0) for u in out_vars)))
-        out_id = next_id[0]
-        next_id[0] += 1
         steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_id, tuple(out_vars), cards,
                           (elim,) if elim is not None else (), (int(card[elim]),) if elim is not None else ()))
         out_strides = []
@@ -377,7 +418,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         union = set().union(*[f.vars for f in inputs]) if inputs else set()
         if final_vars is not None:
             assert union == set(final_vars), (union, final_vars)
-            return emit(inputs, None, list(final_vars))
+            return emit(inputs, None, list(final_vars), may_lift=False)
         out_set = union - {elim}
         return emit(inputs, elim, axis_order(inputs, out_set))
 

@@ -205,3 +205,27 @@ def test_chain_collapses_to_few_launches():
         assert np.allclose(program_interp.run(plan.words, plan.table_blob64, codes, n_rows=3),
                            program_interp.run(ref.words, ref.table_blob64, codes, n_rows=3), rtol=1e-12)
         assert len(plan.steps) <= len(ref.steps)
+
+
+def test_deferred_evidence_instantiation_keeps_answers_and_cuts_row_work():
+    """Products of tables only are computed once as tables that keep their evidence axes
+    (flat launches); only launches that touch a per-row factor stay batched."""
+    for name in ("grid10x10", "asia_1m", "dag50"):
+        wl = workloads.WORKLOADS[name]()
+        bn = wl.build()
+        net = bn._compiled
+        q, e = [net.index[v] for v in wl.query], [net.index[v] for v in wl.evidence]
+        lifted = planner.build_plan(net, q, e)
+        direct = planner.build_plan(net, q, e, lift_evidence=False)
+        nb = lambda p: sum(st.kind == planner.KIND_BATCHED for st in p.steps)
+        assert nb(lifted) < nb(direct) and len(lifted.steps) == len(direct.steps)
+        assert lifted.bytes_per_row() < direct.bytes_per_row()
+        # the tables that keep evidence axes stay within the shared-memory staging size
+        for st in lifted.steps:
+            if st.kind == planner.KIND_FLAT:
+                assert int(np.prod(st.cards, dtype=np.int64)) <= planner.LIFT_MAX
+        assert lifted.steps[-1].kind == planner.KIND_BATCHED  # the posterior itself is per row
+        codes = wl.codes(bn, 7, seed=4)
+        a = program_interp.run(lifted.words, lifted.table_blob64, codes)
+        b = program_interp.run(direct.words, direct.table_blob64, codes)
+        assert np.allclose(a, b, rtol=1e-12, atol=0)
