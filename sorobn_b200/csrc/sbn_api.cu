@@ -64,6 +64,7 @@ struct StepDesc {
     std::vector<int> cards;
     std::vector<int> ecards;     // cardinality per eliminated variable
     int64_t zoff_pos = -1;       // >= 0: int32 offset of the [n_in][cx] joint-state offset table
+    int64_t zoff_tiled_pos = -1; // the same table with rows in the tiled kernel's input order
     std::vector<InDesc> in;
     // tiled fast path (sbn_step_tiled): tile edge, tile count, offset-table position
     int tile = 0;            // 0 = not eligible, use sbn_step_batched
@@ -329,6 +330,15 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         st.order.insert(st.order.end(), as.begin(), as.end());
         st.order.insert(st.order.end(), bs.begin(), bs.end());
         st.order.insert(st.order.end(), cs.begin(), cs.end());
+        if (st.zoff_pos >= 0) {
+            // the tiled kernel sees its inputs in `order`: give it the offset rows in that order
+            st.zoff_tiled_pos = static_cast<int64_t>(words->size());
+            for (int slot : st.order)
+                for (int z = 0; z < st.cx; ++z) {
+                    const int32_t v = (*words)[static_cast<size_t>(st.zoff_pos) + static_cast<size_t>(slot) * st.cx + z];
+                    words->push_back(v);
+                }
+        }
         // tile edge: least padding waste, ties to the larger tile
         int best_t = 2;
         double best_w = 1e30;
@@ -411,6 +421,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     q->n_axes = static_cast<int32_t>(st.cards.size());
     q->cx = st.cx;
     q->zoff = st.zoff_pos >= 0 ? P->d_tile_off + st.zoff_pos : nullptr;
+    if (st.kind == 1 && st.tile > 0 && P->use_tiled && st.zoff_tiled_pos >= 0) q->zoff = P->d_tile_off + st.zoff_tiled_pos;
     q->n_out = static_cast<int32_t>(st.n_out);
     for (size_t j = 0; j < st.cards.size(); ++j) q->card[j] = st.cards[j];
     int smem = 0;
