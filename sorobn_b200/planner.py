@@ -60,7 +60,7 @@ MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
 TILE_EDGE = 5  # largest register-tile edge of sbn_step_tiled
 MAX_ELIM = 3  # variables summed out by one launch (SBN_MAX_ELIM)
 MAX_Z = 256  # joint states of the variables summed out by one launch
-LIFT_MAX = 16384  # entries of a table that keeps evidence axes (64 KB: still staged in shared memory)
+LIFT_MAX = int(os.environ.get("SOROBN_B200_LIFT_MAX", "16384"))  # entries of a table that keeps evidence axes
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
