@@ -60,7 +60,11 @@ MAX_EV = 8  # evidence axes per input (SBN_MAX_EV)
 TILE_EDGE = 5  # largest register-tile edge of sbn_step_tiled
 MAX_ELIM = 3  # variables summed out by one launch (SBN_MAX_ELIM)
 MAX_Z = 256  # joint states of the variables summed out by one launch
-LIFT_MAX = int(os.environ.get("SOROBN_B200_LIFT_MAX", "16384"))  # entries of a table that keeps evidence axes
+# Largest table (entries) that may keep evidence axes.  Swept on B200: 4096 is best on all three
+# benchmark networks (grid 4.21 ms against 4.34 ms without and 4.38 ms at 16384, where a consumer
+# ends up gathering from a 62 KB table for every output).
+LIFT_MAX = int(os.environ.get("SOROBN_B200_LIFT_MAX", "4096"))
+TILED_MAX_IN = 4  # inputs of one launch of the tiled kernel (csrc: kTiledMaxIn)
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
@@ -406,8 +410,37 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
                     best_key, best = key, (a0, a1)
         return [best[0], best[1]] + [u for u in tail if u not in best]
 
-    def product_chain(inputs, elim, final_vars=None):
+    def lifted_size(fs):
+        vs = set().union(*[f.vars for f in fs])
+        cols = {(col, c) for f in fs for col, _, c in f.ev}
+        return int(np.prod([card[u] for u in vs], dtype=np.int64)) * int(np.prod([c for _, c in cols], dtype=np.int64))
+
+    def combine_tables(inputs):
+        """A launch with more than TILED_MAX_IN factors falls off the tiled kernel.  When the
+        surplus is small tables, multiply those together first: a table-only product is an
+        evidence-independent flat launch (see `emit`), and the big launch then gathers one
+        value where it gathered several."""
         inputs = list(inputs)
+        if mode != MODE_BATCHED or not lift_evidence:
+            return inputs
+        while len(inputs) > TILED_MAX_IN:
+            tabs = [f for f in inputs if not f.batched]
+            best = None
+            for i in range(len(tabs)):
+                for j in range(i + 1, len(tabs)):
+                    sz = lifted_size([tabs[i], tabs[j]])
+                    n_cols = len({col for f in (tabs[i], tabs[j]) for col, _, _ in f.ev})
+                    if sz <= LIFT_MAX and n_cols <= MAX_EV and (best is None or sz < best[0]):
+                        best = (sz, tabs[i], tabs[j])
+            if best is None:
+                break
+            _, fa, fb = best
+            inputs = [f for f in inputs if f is not fa and f is not fb]
+            inputs.append(emit([fa, fb], None, sorted(set(fa.vars) | set(fb.vars))))
+        return inputs
+
+    def product_chain(inputs, elim, final_vars=None):
+        inputs = combine_tables(inputs)
         # bayes_net.py:256 reduces pairwise; fuse up to max_in factors per launch and
         # fold the smallest ones first when there are more
         while len(inputs) > max_in:
