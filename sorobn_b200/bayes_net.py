@@ -18,7 +18,7 @@ and `fit` / `partial_fit` / `sample` are outside this path (scope tab
 from __future__ import annotations
 
 import graphlib
-from collections import defaultdict
+from collections import OrderedDict, defaultdict
 
 import numpy as np
 import pandas as pd
@@ -71,7 +71,10 @@ class BayesNet:
         self.P = {}
         self._P_sizes = {}
         self._compiled = None
-        self._engine_cache = {}
+        # compiled device programs, one per (query vars, evidence vars, mode); least recently
+        # used ones are dropped (their streams, graph and scratch are freed with them)
+        self._engine_cache = OrderedDict()
+        self.max_cached_programs = 128
 
     # ------------------------------------------------------------------ structure
     def ancestors(self, node):
@@ -171,7 +174,7 @@ class BayesNet:
             # The reference tolerates a partially specified network until a query
             # touches the hole; keep that: compile lazily once everything is there.
             self._compiled = None
-            self._engine_cache = {}
+            self._engine_cache = OrderedDict()
             return
         seen = {n: set() for n in self.nodes}
         for node, series in self.P.items():
@@ -202,7 +205,7 @@ class BayesNet:
             parents=[[vid[p] for p in self.parents.get(n, [])] for n in self.nodes],
             cpt=cpts,
         )
-        self._engine_cache = {}
+        self._engine_cache = OrderedDict()
 
     # ---------------------------------------------------------------------- query
     def _plan(self, query, evidence_vars, mode):
@@ -224,6 +227,11 @@ class BayesNet:
             # single-event programs run in float64 (latency-bound anyway); batches in float32
             hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT)))
             self._engine_cache[key] = hit
+            while len(self._engine_cache) > self.max_cached_programs:
+                _, (_, old) = self._engine_cache.popitem(last=False)
+                old.close()
+        else:
+            self._engine_cache.move_to_end(key)
         return hit
 
     def _encode_events(self, evidence_vars, columns):
