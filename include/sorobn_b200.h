@@ -112,7 +112,8 @@ int sbn_program_set_graph(sbn_program *prog, int enabled);
 
 /* Select the step kernel: 0 = the plain one-output-per-iteration kernel (general
  * fallback, cross-check in tests); 1 or 2 = register-tiled kernel with the operand
- * preload schedule where available (default); 4 = tiled, x-loop schedule only. */
+ * preload schedule where available (default); 4 = tiled, x-loop schedule only; 5 = tiled
+ * without the shared-memory slab variant for expanding products. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* Pinned host memory for evidence / posterior staging buffers. */

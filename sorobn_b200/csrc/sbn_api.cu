@@ -72,6 +72,12 @@ struct StepDesc {
     std::vector<int> order;      // kernel input slot -> index into `in` (U, then A, then B)
     int64_t n_tiles = 0;
     int64_t tile_off_pos = 0;  // int32 offset into sbn_program::d_tile_off
+    // slab variant (expanding products): tiles grouped by the digits A and B share
+    bool slab = false;
+    int slab_ma = 0, n_slab = 0;
+    int64_t slab_off_pos = 0;
+    int64_t slab_tile_off_pos = 0;  // tile table in slab order (rows of n_in + 5 words)
+    int64_t tiles_per_super = 0, n_super = 0;
 };
 struct Slot {
     bool batched;
@@ -112,6 +118,7 @@ struct sbn_program {
 
     bool use_graph = true;
     bool use_tiled = true;
+    bool use_slab = true;
     int tiled_v = 2;  // 2 = preload schedule where available (default), 4 = always the x-loop schedule
     cudaGraphExec_t exec = nullptr;
     struct {
@@ -263,6 +270,100 @@ constexpr int kTiledMaxIn = 4;
 constexpr int kRowsPerThread = 2;
 constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 
+constexpr int kSlabThreads = 64;                 // CTA size of the slab variant (x kRowsPerThread rows)
+constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one slab may take
+
+// Slab variant of the tiled kernel: eligible when the launch multiplies one batched factor on
+// the A side with one on the B side (plus at most one table without tile axes), both with
+// private axes beyond the tile.  Emits the tile table in slab order (shared digits, then the
+// B-private digits and B blocks, then the A-private digits and A blocks) and the slab's entry
+// offsets.  Returns false when the step does not qualify (the caller then emits the plain
+// tile table).
+bool plan_slab(sbn_program *P, StepDesc &st, int T, std::vector<int32_t> *words) {
+    (void)P;
+    const int n_axes = static_cast<int>(st.cards.size());
+    const int n_in = static_cast<int>(st.in.size());
+    if (st.nc != 0 || st.na != 1 || st.nb != 1 || st.nu > 1 || n_in > 3 || n_axes < 3) return false;
+    if (st.ecards.size() != 1) return false;
+    if (!(st.cx == T || (T == 4 && st.cx == 8))) return false;  // needs the preload schedule
+    const InDesc &A = st.in[st.order[st.nu]], &B = st.in[st.order[st.nu + 1]];
+    if (!A.batched || !B.batched) return false;
+    const int c0 = st.cards[0], c1 = st.cards[1];
+    std::vector<int> pa, pb, sh;  // axes >= 2: private to A, private to B, shared
+    int64_t n_pa = 1, n_pb = 1, n_sh = 1;
+    for (int j = 2; j < n_axes; ++j) {
+        const bool ha = A.strides[j] != 0, hb = B.strides[j] != 0;
+        if (ha && !hb) { pa.push_back(j); n_pa *= st.cards[j]; }
+        else if (hb && !ha) { pb.push_back(j); n_pb *= st.cards[j]; }
+        else { sh.push_back(j); n_sh *= st.cards[j]; }
+    }
+    if (n_pa == 1 || n_pb == 1) return false;  // nothing is re-read: the plain tile walk is optimal
+    const int64_t ma = static_cast<int64_t>(c0) * n_pa;
+    const int64_t n_slab = ma * st.cx;
+    if (n_slab * kSlabThreads * kRowsPerThread * 4 > kSlabSmemMax) return false;
+    const int n_ta = (c0 + T - 1) / T, n_tb = (c1 + T - 1) / T;
+    const int64_t tiles_per_super = n_pb * n_tb * n_pa * n_ta;
+    if (n_sh * tiles_per_super * (n_in + 5) > kTileTableMax) return false;
+
+    st.slab = true;
+    st.slab_ma = static_cast<int>(ma);
+    st.n_slab = static_cast<int>(n_slab);
+    st.n_super = n_sh;
+    st.tiles_per_super = tiles_per_super;
+    // slab entry k = x * ma + (d0 + c0 * pa_index)  ->  element offset inside A (shared digits 0)
+    st.slab_off_pos = static_cast<int64_t>(words->size());
+    for (int x = 0; x < st.cx; ++x)
+        for (int64_t ia = 0; ia < n_pa; ++ia)
+            for (int d0 = 0; d0 < c0; ++d0) {
+                int64_t off = static_cast<int64_t>(x) * A.sx + static_cast<int64_t>(d0) * A.strides[0];
+                int64_t r = ia;
+                for (int j : pa) {
+                    off += (r % st.cards[j]) * A.strides[j];
+                    r /= st.cards[j];
+                }
+                words->push_back(static_cast<int32_t>(off));
+            }
+    // NOTE the loop nest above emits (x, ia, d0) with d0 fastest: index = x*ma + ia*c0 + d0
+
+    std::vector<int64_t> out_stride(n_axes, 1);
+    for (int j = 1; j < n_axes; ++j) out_stride[j] = out_stride[j - 1] * st.cards[j - 1];
+    st.slab_tile_off_pos = static_cast<int64_t>(words->size());
+    std::vector<int> digit(n_axes, 0);
+    for (int64_t is = 0; is < n_sh; ++is) {
+        int64_t r = is;
+        for (int j : sh) { digit[j] = static_cast<int>(r % st.cards[j]); r /= st.cards[j]; }
+        int64_t a_super = 0;
+        for (int j : sh) a_super += static_cast<int64_t>(digit[j]) * A.strides[j];
+        for (int64_t ib = 0; ib < n_pb; ++ib) {
+            r = ib;
+            for (int j : pb) { digit[j] = static_cast<int>(r % st.cards[j]); r /= st.cards[j]; }
+            for (int tb = 0; tb < n_tb; ++tb) {
+                for (int64_t ia = 0; ia < n_pa; ++ia) {
+                    r = ia;
+                    for (int j : pa) { digit[j] = static_cast<int>(r % st.cards[j]); r /= st.cards[j]; }
+                    for (int ta = 0; ta < n_ta; ++ta) {
+                        const int na = std::min(T, c0 - ta * T), nb = std::min(T, c1 - tb * T);
+                        int64_t o = static_cast<int64_t>(ta) * T + static_cast<int64_t>(tb) * T * c0;
+                        for (int j = 2; j < n_axes; ++j) o += static_cast<int64_t>(digit[j]) * out_stride[j];
+                        words->push_back(static_cast<int32_t>(o));
+                        words->push_back(na | (nb << 8));
+                        for (int i = 0; i < n_in; ++i) {
+                            const InDesc &in = st.in[st.order[i]];
+                            int64_t off = static_cast<int64_t>(ta) * T * in.strides[0] + static_cast<int64_t>(tb) * T * in.strides[1];
+                            for (int j = 2; j < n_axes; ++j) off += static_cast<int64_t>(digit[j]) * in.strides[j];
+                            words->push_back(static_cast<int32_t>(off));
+                        }
+                        words->push_back(static_cast<int32_t>(is));
+                        words->push_back(static_cast<int32_t>(ta * T + static_cast<int64_t>(c0) * ia));
+                        words->push_back(static_cast<int32_t>(a_super));
+                    }
+                }
+            }
+        }
+    }
+    return true;
+}
+
 // Host half of the tiled kernel: pick the tile edge and precompute, for every tile, the
 // output entry and each input's element offset (the row-invariant mixed-radix
 // decomposition, hoisted out of the kernel).
@@ -359,6 +460,8 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         if (n_tiles * (n_in + 2) > kTileTableMax) continue;
         st.tile = T;
         st.n_tiles = n_tiles;
+        st.slab = false;
+        plan_slab(P, st, T, words);  // optional second tile table in slab order
         st.tile_off_pos = static_cast<int64_t>(words->size());
         std::vector<int64_t> off(n_in);
         for (int64_t r = 0; r < rest; ++r) {
@@ -473,6 +576,21 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         q->n_bblocks = static_cast<int32_t>(n_rblocks);
         q->tile1 = 0;
         q->n_tile1 = 0;
+        if (st.slab && P->tiled_v == 2 && P->use_slab) {
+            // whole groups per CTA; 64-thread CTAs (128 rows) so that the slab fits shared memory
+            const int64_t rows_slab = static_cast<int64_t>(kSlabThreads) * kRowsPerThread;
+            const int64_t n_rb = (n_rows + rows_slab - 1) / rows_slab;
+            const int64_t groups = std::max<int64_t>(1, std::min<int64_t>(st.n_super, target / std::max<int64_t>(1, n_rb)));
+            const int64_t supers_per_cta = (st.n_super + groups - 1) / groups;
+            q->tiles_per_cta = static_cast<int32_t>(supers_per_cta * st.tiles_per_super);
+            q->n_chunks = static_cast<int32_t>((st.n_super + supers_per_cta - 1) / supers_per_cta);
+            q->n_bblocks = static_cast<int32_t>(n_rb);
+            q->tile_off = P->d_tile_off + st.slab_tile_off_pos;
+            q->slab_off = P->d_tile_off + st.slab_off_pos;
+            q->n_slab = st.n_slab;
+            q->slab_ma = st.slab_ma;
+            q->slab_smem_off = static_cast<int32_t>(round_up(q->smem_floats, 4));
+        }
     } else if (st.kind == 1) {
         const int c0 = q->n_axes > 0 ? q->card[0] : 1;
         const int c1 = q->n_axes > 1 ? q->card[1] : 1;
@@ -584,7 +702,36 @@ cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t gri
     return cudaGetLastError();
 }
 
+template <int NU>
+cudaError_t launch_slab(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
+    const size_t smem = (static_cast<size_t>(q.slab_smem_off) + static_cast<size_t>(q.n_slab) * kSlabThreads * kV) * 4;
+    const dim3 g(static_cast<unsigned>(grid)), b(kSlabThreads);
+    switch (tile) {
+        case 2: sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true><<<g, b, smem, stream>>>(q); break;
+        case 3: sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true><<<g, b, smem, stream>>>(q); break;
+        case 5: sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true><<<g, b, smem, stream>>>(q); break;
+        case 4:
+            if (q.cx == 8) sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true><<<g, b, smem, stream>>>(q);
+            else sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true><<<g, b, smem, stream>>>(q);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int NU>
+cudaError_t set_slab_attr() {
+    const int bytes = static_cast<int>(kSlabSmemMax) + SBN_SMEM_BUDGET;
+    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
+}
+
 cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int64_t grid, cudaStream_t stream) {
+    if (q.slab_off != nullptr) return st.nu == 0 ? launch_slab<0>(q, st.tile, grid, stream) : launch_slab<1>(q, st.tile, grid, stream);
     const int key = st.nu * 1000 + st.na * 100 + st.nb * 10 + st.nc;
     // the preload schedule keeps every operand of a tile in registers: only for <= 3 inputs,
     // one eliminated variable
@@ -612,7 +759,8 @@ cudaError_t set_tiled_attr_c() {
     return e;
 }
 cudaError_t set_tiled_attrs() {
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = set_slab_attr<0>();
+    if (e == cudaSuccess) e = set_slab_attr<1>();
 #define X(U, A, B, C) \
     if (e == cudaSuccess) e = set_tiled_attr_c<U, A, B, C>();
     SBN_TILED_COMBOS(X)
@@ -1106,6 +1254,7 @@ int sbn_program_set_tiled(sbn_program *P, int enabled) {
     }
     P->use_tiled = enabled != 0;
     if (enabled == 4 || enabled == 2) P->tiled_v = enabled;
+    P->use_slab = enabled != 5;
     return SBN_OK;
 }
 

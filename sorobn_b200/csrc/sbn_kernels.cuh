@@ -62,6 +62,12 @@ struct SbnStep {
     int32_t n_chunks;                 // tiled kernel: ceil(n_tiles / tiles_per_cta)
     const int32_t *zoff;              // several eliminated variables: [n_in][cx] element offsets of
                                       // their joint states (nullptr: one variable, offset = x * sx)
+    // slab variant of the tiled kernel (expanding products, see sbn_step_tiled<..., SLAB = true>)
+    const int32_t *slab_off;          // [n_slab] element offsets of the A-side slab entries
+    int32_t n_slab;                   // cx * slab_ma
+    int32_t slab_ma;                  // A-side entries per eliminated state in one slab
+    int32_t slab_smem_off;            // float offset of the slab inside dynamic shared memory
+    int32_t pad2_;
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -293,13 +299,24 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 // With a C-side input (T*T loads per x already) only the x-loop schedule is built.
 // When several variables are eliminated at once, x runs over their joint states and the
 // per-input element offset comes from `zoff` instead of x * sx.
-template <int NU, int NA, int NB, int NC, int T, int V, int CX>
+//
+// SLAB = true is the variant for *expanding* products (both the A-side and the B-side batched
+// factor have private axes beyond the tile, e.g. 3125 <- B625 x B625): every A entry is needed
+// by several B blocks and vice versa, and the caches do not hold the 250 KB per CTA that would
+// take.  Tiles are grouped by the digits the two factors share; for one such group a thread
+// first copies ITS rows of the whole A-side slab into its own shared-memory column (no
+// barrier: a thread only ever reads back what it wrote), then walks the group's tiles reading
+// A from shared memory and B blocks through registers (reloaded only when the block
+// changes).  Both factors are then read from HBM exactly once.
+template <int NU, int NA, int NB, int NC, int T, int V, int CX, bool SLAB = false>
 __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 : 4)))
     sbn_step_tiled(const __grid_constant__ SbnStep p) {
     constexpr int N_IN = NU + NA + NB + NC;
     constexpr int TB = (NB > 0 || NC > 0) ? T : 1;  // no input with axis 1: single-axis output
+    constexpr int ROW_WORDS = N_IN + 2 + (SLAB ? 3 : 0);  // int32 per tile_off row
     static_assert(NC <= 1, "one input may span both tile axes");
     static_assert(CX == 0 || NC == 0, "the preload schedule does not cover a C-side input");
+    static_assert(!SLAB || (NA == 1 && NB == 1 && NC == 0 && CX > 0), "slab variant: one A, one B, preload");
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -326,7 +343,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
     // few row blocks, so operands shared between tiles are re-read from L2, not from HBM.
     const int rblock = blockIdx.x / p.n_chunks;
     const int chunk = blockIdx.x % p.n_chunks;
-    const int b = (rblock * SBN_TILED_THREADS + threadIdx.x) * V;
+    const int b = (rblock * static_cast<int>(blockDim.x) + threadIdx.x) * V;
     const bool live = b < p.n_rows;  // b % V == 0 and ld % 32 == 0: the vector stays inside the pitch
 
     const float *gsrc[N_IN];  // global, row b (batched inputs)
@@ -372,14 +389,45 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
         }
     };
 
+    // slab state: this thread's column of the A-side slab, the B block kept in registers
+    float *const slab = s_tab + p.slab_smem_off + threadIdx.x * V;
+    const int slab_pitch = static_cast<int>(blockDim.x) * V;  // floats between consecutive slab entries
+    int cur_slab = -1, cur_bblock = -1;
+    float rb_keep[SLAB ? CX : 1][SLAB ? TB : 1][V];
+
     for (int t = t_begin; t < t_end; ++t) {
-        const int32_t *row = p.tile_off + static_cast<int64_t>(t) * (N_IN + 2);
+        const int32_t *row = p.tile_off + static_cast<int64_t>(t) * ROW_WORDS;
         const int o_base = __ldg(row);
         const int nab = __ldg(row + 1);
         const int na = nab & 0xff, nb = nab >> 8;
         int base[N_IN];
 #pragma unroll
         for (int i = 0; i < N_IN; ++i) base[i] = __ldg(row + 2 + i);
+        int a_slab_idx = 0;
+        if constexpr (SLAB) {
+            const int slab_id = __ldg(row + N_IN + 2);
+            a_slab_idx = __ldg(row + N_IN + 3);
+            if (slab_id != cur_slab) {
+                // copy this thread's rows of the group's A-side slab: global -> registers -> shared
+                const int a_super = __ldg(row + N_IN + 4);
+                constexpr int i = NU;  // the A-side input
+                for (int k0s = 0; k0s < p.n_slab; k0s += 8) {
+                    float tmp[8][V];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (k0s + u < p.n_slab)
+                            sbn_ldv<V>(tmp[u], gsrc[i] + static_cast<int64_t>(a_super + __ldg(p.slab_off + k0s + u)) * ld);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (k0s + u < p.n_slab) {
+                            typename SbnVec<V>::type v;
+                            memcpy(&v, tmp[u], sizeof v);
+                            *reinterpret_cast<typename SbnVec<V>::type *>(slab + (k0s + u) * slab_pitch) = v;
+                        }
+                }
+                cur_slab = slab_id;
+            }
+        }
 
         float acc[T][TB][V];
 #pragma unroll
@@ -402,23 +450,49 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
             if constexpr (CX > 0) {
                 // ---- preload schedule: all loads first ...
                 float ra[NA > 0 ? NA : 1][CX][T][V], rb[NB > 0 ? NB : 1][CX][TB][V], ru[NU > 0 ? NU : 1][CX][V];
+                if constexpr (SLAB) {
+                    // B block: registers, reloaded only when the block changes
+                    constexpr int ib = NU + NA;
+                    if (base[ib] != cur_bblock) {
+                        const int s1 = p.in[ib].stride[1], sx = p.in[ib].sx;
 #pragma unroll
-                for (int j = 0; j < NA; ++j) {
-                    const int i = NU + j;
-                    const int s0 = p.in[i].stride[0], sx = p.in[i].sx;
+                        for (int x = 0; x < CX; ++x)
 #pragma unroll
-                    for (int x = 0; x < CX; ++x)
-#pragma unroll
-                        for (int d = 0; d < T; ++d) fetch(i, base[i] + x * sx + k0[d] * s0, ra[j][x][d]);
-                }
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int i = NU + NA + j;
-                    const int s1 = p.in[i].stride[1], sx = p.in[i].sx;
+                            for (int d = 0; d < TB; ++d) fetch(ib, base[ib] + x * sx + k1[d] * s1, rb_keep[x][d]);
+                        cur_bblock = FULL ? base[ib] : -1;  // a clamped (partial) block is not reusable
+                    }
 #pragma unroll
                     for (int x = 0; x < CX; ++x)
 #pragma unroll
-                        for (int d = 0; d < TB; ++d) fetch(i, base[i] + x * sx + k1[d] * s1, rb[j][x][d]);
+                        for (int d = 0; d < TB; ++d)
+#pragma unroll
+                            for (int l = 0; l < V; ++l) rb[0][x][d][l] = rb_keep[x][d][l];
+                    // A block: this thread's column of the slab
+#pragma unroll
+                    for (int x = 0; x < CX; ++x)
+#pragma unroll
+                        for (int d = 0; d < T; ++d) {
+                            sbn_ldv<V>(ra[0][x][d], slab + (a_slab_idx + k0[d] + x * p.slab_ma) * slab_pitch);
+                        }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NA; ++j) {
+                        const int i = NU + j;
+                        const int s0 = p.in[i].stride[0], sx = p.in[i].sx;
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < T; ++d) fetch(i, base[i] + x * sx + k0[d] * s0, ra[j][x][d]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int i = NU + NA + j;
+                        const int s1 = p.in[i].stride[1], sx = p.in[i].sx;
+#pragma unroll
+                        for (int x = 0; x < CX; ++x)
+#pragma unroll
+                            for (int d = 0; d < TB; ++d) fetch(i, base[i] + x * sx + k1[d] * s1, rb[j][x][d]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {

@@ -398,3 +398,37 @@ def test_merged_sum_outs_match_unmerged_program_on_device():
         fp = planner.build_plan(net, q, e, mode=planner.MODE_FLAT, merge_sum_outs=False)
         one = np.ascontiguousarray(codes[:, :1])
         assert np.allclose(engine.Program(fm, f64=True).run(one, 1), engine.Program(fp, f64=True).run(one, 1), rtol=1e-12)
+
+
+def test_slab_variant_matches_plain_tile_walk():
+    """Expanding products (both batched operands have private axes) run through the
+    shared-memory slab variant; with it switched off (mode 5) the same program must give the
+    same posteriors to float32 rounding, and both must match the oracle."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet, engine, planner, synthetic, workloads
+
+    wl = workloads.grid10x10()
+    jobs = [(wl.build(), wl.query, wl.evidence, None, 6000)]
+    for cards, seed in ((4, 5), (3, 6), ((2, 5, 3), 7)):
+        spec = synthetic.grid(5, 5, cards if isinstance(cards, int) else 3, seed=seed)
+        jobs.append((synthetic.load(spec, BayesNet), (spec.nodes[-1],), tuple(spec.nodes[1:9:4]), spec, 900))
+    for bn, query, evidence, spec, B in jobs:
+        net = bn._compiled
+        plan = planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evidence])
+        if spec is None:
+            codes = wl.codes(bn, B, seed=31)
+        else:
+            ev = synthetic.random_events(spec, list(evidence), B, seed=31)
+            codes = np.stack([ev[v].to_numpy().astype(np.uint8) for v in evidence])
+        prog = engine.Program(plan)
+        with_slab = prog.run(codes, B).copy()
+        prog.set_tiled(5)
+        without = prog.run(codes, B).copy()
+        assert np.isfinite(with_slab).all()
+        assert np.allclose(with_slab, without, rtol=2e-6, atol=1e-30)
+        dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+        order = [net.names[v] for v in plan.order]
+        for b in range(0, B, B // 7):
+            evd = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(evidence)}
+            want = ve_oracle.query(dn, *query, event=evd, order=order)[1].reshape(-1)
+            assert rel_err(with_slab[:, b], want) < RTOL
