@@ -411,20 +411,16 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
                 // copy this thread's rows of the group's A-side slab: global -> registers -> shared
                 const int a_super = __ldg(row + N_IN + 4);
                 constexpr int i = NU;  // the A-side input
-                for (int k0s = 0; k0s < p.n_slab; k0s += 8) {
-                    float tmp[8][V];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (k0s + u < p.n_slab)
-                            sbn_ldv<V>(tmp[u], gsrc[i] + static_cast<int64_t>(a_super + __ldg(p.slab_off + k0s + u)) * ld);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (k0s + u < p.n_slab) {
-                            typename SbnVec<V>::type v;
-                            memcpy(&v, tmp[u], sizeof v);
-                            *reinterpret_cast<typename SbnVec<V>::type *>(slab + (k0s + u) * slab_pitch) = v;
-                        }
+                // asynchronous copies (cp.async -> LDGSTS): no staging registers, every entry of
+                // the slab in flight at once; visible to this thread after wait_group
+                for (int k = 0; k < p.n_slab; ++k) {
+                    const float *src = gsrc[i] + static_cast<int64_t>(a_super + __ldg(p.slab_off + k)) * ld;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sbn_smem_u32(slab + k * slab_pitch)),
+                                 "l"(src), "n"(V * 4)
+                                 : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 cur_slab = slab_id;
             }
         }
