@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 3
+#define SBN_ABI_VERSION 4
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -89,6 +89,14 @@ int sbn_program_run_host(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, in
 /* float64 programs (n_rows must be 1). */
 int sbn_program_run_host_f64(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *out,
                              int64_t ld_out);
+
+/* P(event) of every evidence row: the normaliser the run divides by (bayes_net.py:790).  This is
+ * what `BayesNet.predict_proba` returns (bayes_net.py:934-962: the full joint, marginalised over
+ * the unobserved variables and looked up at the row) without ever building the joint.  The program
+ * may have no query variable at all (planner: allow_empty_query).  prob[b], b < n_rows; NaN marks
+ * a row below the float32 range (re-run it with a float64 program). */
+int sbn_program_evidence_host(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *prob);
+int sbn_program_evidence_host_f64(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *prob);
 
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = default
  * stream).  n_rows must not exceed the reserved chunk size. */

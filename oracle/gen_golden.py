@@ -173,6 +173,30 @@ def main():
             json.dump({"network": name, "kind": "example", "nodes": ref_bn.nodes, "cases": cases}, f)
         print(f"{name}: {len(cases)} cases in {time.time() - t:.1f}s")
 
+    # ---- predict_proba (bayes_net.py:934-962) on the example networks ----------------
+    import pandas as pd
+
+    for name, spec in ({} if only_workload else examples.NETWORKS).items():
+        ref_bn = examples.build(spec, cls=ref.BayesNet)
+        fjd = ref_bn.full_joint_dist()
+        nodes = list(fjd.index.names)
+        cases = []
+        # every row of the joint (all variables observed)
+        full = pd.DataFrame(fjd.index.tolist(), columns=nodes)
+        cases.append({"columns": nodes, "rows": [[jsonable(v) for v in r] for r in full.to_numpy().tolist()],
+                      "prob": [float(x) for x in ref_bn.predict_proba(full).to_numpy()]})
+        # marginals over subsets of 2 and 3 columns (one column hits a reference quirk: it
+        # returns the whole marginal instead of per-row values)
+        for k in (2, 3):
+            for cols in list(itertools.combinations(nodes, k))[:8]:
+                sub = full[list(cols)].drop_duplicates().reset_index(drop=True)
+                prob = ref_bn.predict_proba(sub)
+                cases.append({"columns": list(cols), "rows": [[jsonable(v) for v in r] for r in sub.to_numpy().tolist()],
+                              "prob": [float(x) for x in prob.to_numpy()]})
+        with open(os.path.join(OUT, f"predict_proba_{name}.json"), "w") as f:
+            json.dump({"network": name, "kind": "predict_proba", "cases": cases}, f)
+        print(f"predict_proba {name}: {len(cases)} cases, {sum(len(c['rows']) for c in cases)} rows")
+
     # ---- synthetic networks ----------------------------------------------------------
     jobs = [
         ("grid4x4s3", ("grid", dict(rows=4, cols=4, n_states=3, seed=11)), 40, (0, 8)),

@@ -58,7 +58,7 @@ def parse(words):
     return hdr, tables, slots, steps
 
 
-def run(words, table_blob, ev_codes, n_rows=None, dtype=np.float64):
+def run(words, table_blob, ev_codes, n_rows=None, dtype=np.float64, return_totals=False):
     """Execute the program.  ev_codes: uint8 array [n_ev, B] (n_rows gives B when
     there are no evidence columns).  Returns the normalised posterior [Q, B]
     (state-major, like the C-ABI's output)."""
@@ -127,4 +127,7 @@ def run(words, table_blob, ev_codes, n_rows=None, dtype=np.float64):
     post = post[:hdr["Q"]]
     total = post.sum(axis=0, keepdims=True, dtype=dtype)
     with np.errstate(invalid="ignore", divide="ignore"):
-        return (post / total).astype(dtype)
+        normalised = (post / total).astype(dtype)
+    if return_totals:  # the normaliser is P(event) per row (sbn_program_evidence_host)
+        return normalised, total.reshape(-1)
+    return normalised

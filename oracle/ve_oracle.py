@@ -37,6 +37,7 @@ __all__ = [
     "pointwise_mul",
     "variable_elimination",
     "query",
+    "evidence_probability",
     "dense_from_pandas",
     "min_fill_order",
 ]
@@ -214,6 +215,27 @@ def variable_elimination(net: DenseNet, query_vars, event: dict, order=None) -> 
     total = posterior.values.sum()
     with np.errstate(invalid="ignore", divide="ignore"):  # P(event) == 0 -> NaN (reference: empty answer)
         return Factor(posterior.vars, posterior.values / total)
+
+
+def evidence_probability(net: DenseNet, event: dict) -> float:
+    """P(event): what `predict_proba` (bayes_net.py:934-962) looks up in the full joint after
+    marginalising the unobserved variables.  Computed by eliminating every non-event variable
+    among the event's ancestors (the others sum to one)."""
+    relevant = set(event)
+    for node in list(relevant):
+        relevant |= net.ancestors(node)
+    factors = []
+    for node in sorted(relevant, key=net.nodes.index):
+        scope = net.scope(node)
+        index = tuple(net.domains[v].index(event[v]) if v in event else slice(None) for v in scope)
+        factors.append(Factor(tuple(v for v in scope if v not in event), np.asarray(net.cpt[node][index], dtype=np.float64)))
+    hidden = relevant - set(event)
+    cards = {v: len(net.domains[v]) for v in net.nodes}
+    for node in min_fill_order([f.vars for f in factors], sorted(hidden, key=net.nodes.index), cards):
+        touching = [f for f in factors if node in f.vars]
+        factors = [f for f in factors if node not in f.vars]
+        factors.append(sum_out(pointwise_mul(touching), node))
+    return float(pointwise_mul(factors).values)
 
 
 def query(net: DenseNet, *query_vars, event: dict, order=None):

@@ -12,12 +12,17 @@ or a GPU `query()` raises.
 `query_many()` is the batched form of `query()` (one posterior per evidence row of a
 DataFrame); it is what the multi-GPU sharding and the benchmark drive.
 
+`predict_proba` / `predict_log_proba` / `full_joint_dist` (bayes_net.py:398-465, :934-973) run
+on the same kernels: the probability of a row is the normaliser of an elimination with the
+row as evidence.
+
 The sampling-based algorithms (gibbs / likelihood / rejection, bayes_net.py:577-737)
 and `fit` / `partial_fit` / `sample` are outside this path (scope table).
 """
 from __future__ import annotations
 
 import graphlib
+import typing
 from collections import OrderedDict, defaultdict
 
 import numpy as np
@@ -221,7 +226,7 @@ class BayesNet:
                 if name not in net.index:
                     raise KeyError(name)
             plan = _planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evidence_vars],
-                                       mode=mode)
+                                       mode=mode, allow_empty_query=True)
             from . import engine  # raises if libsorobn_b200.so cannot be loaded
 
             # single-event programs run in float64 (latency-bound anyway); batches in float32
@@ -322,6 +327,54 @@ class BayesNet:
         if bad.any():
             out.loc[events.index[bad]] = np.nan
         return out
+
+    # ------------------------------------------------------- joint / likelihood of rows
+    def full_joint_dist(self, event: dict = None, keep_zeros=False) -> pd.Series:
+        """The normalised product of every CPT (bayes_net.py:398-465), computed on the GPU
+        as one exact query over all the variables with no evidence.  Like the reference the
+        levels are sorted by name and combinations of probability zero are left out unless
+        `keep_zeros`.  Practical for small networks only (the joint has prod(card) rows)."""
+        names = sorted(self.nodes)
+        plan, program = self._plan(tuple(names), (), _planner.MODE_FLAT)
+        post = program.run(np.zeros((0, 1), dtype=np.uint8), 1)[:, 0].astype(np.float64)
+        fjd = pd.Series(post, index=self._answer_index(plan), name=f"P({', '.join(map(str, names))})")
+        return fjd if keep_zeros else fjd[post > 0]
+
+    def predict_proba(self, X: typing.Union[dict, pd.DataFrame]):
+        """Probability of each row of `X` (bayes_net.py:934-962).
+
+        The reference builds the full joint, sums out the columns `X` lacks and looks the
+        rows up.  Here P(row) is the normaliser of a variable elimination with the row as
+        evidence and no query variable: same number, no joint, any network size.  Rows of
+        probability zero give 0.0 (the reference's joint has no such row and raises
+        KeyError).  With a single column the reference returns the whole marginal instead
+        of per-row values; this returns per-row values in every case."""
+        if isinstance(X, dict):
+            return self.predict_proba(pd.DataFrame([X])).iloc[0]
+        ev_vars = tuple(sorted(X.columns))
+        n = len(X.index)
+        name = f"P({', '.join(map(str, ev_vars))})"
+        if len(ev_vars) == 1:
+            index = pd.Index(X[ev_vars[0]], name=ev_vars[0])
+        else:
+            index = pd.MultiIndex.from_frame(X[list(ev_vars)])
+        if n == 0:
+            return pd.Series([], index=index, name=name, dtype=np.float64)
+        plan, program = self._plan((), ev_vars, _planner.MODE_BATCHED)
+        codes, bad = self._encode_events(ev_vars, [X[v].to_numpy() for v in ev_vars])
+        prob = program.evidence(codes, n).astype(np.float64)
+        suspect = np.isnan(prob) & ~bad
+        if suspect.any():  # below the float32 range (or exactly zero): settle in float64
+            _, flat = self._plan((), ev_vars, _planner.MODE_FLAT)
+            for b in np.nonzero(suspect)[0]:
+                prob[b] = flat.evidence(np.ascontiguousarray(codes[:, b:b + 1]), 1)[0]
+        prob[np.isnan(prob) | bad] = 0.0
+        return pd.Series(prob, index=index, name=name)
+
+    def predict_log_proba(self, X: typing.Union[dict, pd.DataFrame]):
+        """Log-likelihood of each row (bayes_net.py:964-973)."""
+        with np.errstate(divide="ignore"):
+            return np.log(self.predict_proba(X))
 
     def impute(self, sample: dict, **query_params) -> pd.Series:
         """Fill the `None` entries of `sample` with their most probable joint value

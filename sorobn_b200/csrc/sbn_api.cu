@@ -105,6 +105,7 @@ struct sbn_program {
     float *d_arena = nullptr;   // batched scratch
     float *d_shared = nullptr;  // unbatched scratch
     int32_t *d_tile_off = nullptr;  // per-step tile offset tables of the tiled kernel
+    float *d_total = nullptr;   // per-row normaliser = P(event) of the last run [ld] (double when f64)
     uint8_t *d_ev = nullptr;    // staging for run_host  [n_ev][ld]
     float *d_out = nullptr;     //                         [Q][ld]   (double when f64)
     cudaStream_t stream = nullptr;
@@ -497,6 +498,8 @@ void free_scratch(sbn_program *P) {
     cudaFree(P->d_arena);
     cudaFree(P->d_ev);
     cudaFree(P->d_out);
+    cudaFree(P->d_total);
+    P->d_total = nullptr;
     P->d_arena = nullptr;
     P->d_ev = nullptr;
     P->d_out = nullptr;
@@ -807,11 +810,12 @@ cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64
     if (P->f64)
         sbn_normalise<double><<<static_cast<unsigned>(grid), threads, 0, stream>>>(
             reinterpret_cast<const double *>(P->slots[P->post_slot].ptr), P->ld, P->post_batched, P->Q,
-            reinterpret_cast<double *>(d_out), ld_out, static_cast<int>(n_rows), 1e-290);
+            reinterpret_cast<double *>(d_out), ld_out, static_cast<int>(n_rows), 1e-290,
+            reinterpret_cast<double *>(P->d_total));
     else
         sbn_normalise<float><<<static_cast<unsigned>(grid), threads, 0, stream>>>(
             P->slots[P->post_slot].ptr, P->ld, P->post_batched, P->Q, d_out, ld_out, static_cast<int>(n_rows),
-            SBN_MIN_TOTAL_F32);
+            SBN_MIN_TOTAL_F32, P->d_total);
     return cudaGetLastError();
 }
 
@@ -1094,6 +1098,7 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
         SBN_CUDA(cudaMemsetAsync(P->d_ev, 0, static_cast<size_t>(P->n_ev) * ld, P->stream));
     }
     SBN_CUDA(cudaMalloc(&P->d_out, static_cast<size_t>(P->Q) * ld * (P->f64 ? 8 : 4)));
+    SBN_CUDA(cudaMalloc(&P->d_total, static_cast<size_t>(ld) * (P->f64 ? 8 : 4)));
     SBN_CUDA(cudaStreamSynchronize(P->stream));  // the memset must not race a caller's stream
     P->reserved_rows = rows;
     P->ld = ld;
@@ -1155,8 +1160,8 @@ static int run_device_impl(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, i
 }
 
 static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, void *out_, int64_t ld_out,
-                           bool f64) {
-    int rc = check_run_args(P, ev, ld_ev, n_rows, out_, ld_out);
+                           bool f64, bool want_totals = false) {
+    int rc = check_run_args(P, ev, ld_ev, n_rows, out_, want_totals ? n_rows : ld_out);
     if (rc != SBN_OK) return rc;
     if (P->f64 != f64) return fail(SBN_E_INVALID, "program precision does not match the run call");
     const size_t elem = f64 ? 8 : 4;
@@ -1175,9 +1180,13 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
                                        P->stream));
         rc = run_device_impl(P, P->d_ev, P->ld, rows, P->d_out, P->ld, P->stream);
         if (rc != SBN_OK) return rc;
-        SBN_CUDA(cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, P->d_out,
-                                   static_cast<size_t>(P->ld) * elem, static_cast<size_t>(rows) * elem,
-                                   static_cast<size_t>(P->Q), cudaMemcpyDeviceToHost, P->stream));
+        if (want_totals)
+            SBN_CUDA(cudaMemcpyAsync(out + r0 * elem, P->d_total, static_cast<size_t>(rows) * elem,
+                                     cudaMemcpyDeviceToHost, P->stream));
+        else
+            SBN_CUDA(cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, P->d_out,
+                                       static_cast<size_t>(P->ld) * elem, static_cast<size_t>(rows) * elem,
+                                       static_cast<size_t>(P->Q), cudaMemcpyDeviceToHost, P->stream));
     }
     SBN_CUDA(cudaStreamSynchronize(P->stream));
     return SBN_OK;
@@ -1190,6 +1199,14 @@ int sbn_program_run_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64
 int sbn_program_run_host_f64(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *out,
                              int64_t ld_out) {
     return run_host_common(P, ev, ld_ev, n_rows, out, ld_out, true);
+}
+
+int sbn_program_evidence_host(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *prob) {
+    return run_host_common(P, ev, ld_ev, n_rows, prob, n_rows, false, true);
+}
+
+int sbn_program_evidence_host_f64(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *prob) {
+    return run_host_common(P, ev, ld_ev, n_rows, prob, n_rows, true, true);
 }
 
 int sbn_program_profile(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out,

@@ -675,14 +675,17 @@ __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ Sbn
 template <typename T>
 __global__ void __launch_bounds__(256)
 sbn_normalise(const T *__restrict__ post, int64_t ld, int post_batched, int Q, T *__restrict__ out, int64_t ld_out,
-              int n_rows, T min_total) {
+              int n_rows, T min_total, T *__restrict__ totals) {
     const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= n_rows) return;
     const int64_t pitch = post_batched ? ld : 1;
     const int64_t base = post_batched ? b : 0;
     T total = T(0);
     for (int q = 0; q < Q; ++q) total += post[q * pitch + base];
+    // the normaliser is P(event) for this row (bayes_net.py:790 divides by it; predict_proba,
+    // bayes_net.py:934, returns it); below min_total it is reported as NaN like the posterior
     const bool ok = total >= min_total;  // false for NaN too
+    if (totals) totals[b] = ok ? total : static_cast<T>(__int_as_float(0x7fc00000));
     const T nan = static_cast<T>(__int_as_float(0x7fc00000));
     for (int q = 0; q < Q; ++q) out[q * ld_out + b] = ok ? post[q * pitch + base] / total : nan;
 }

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class EngineError(RuntimeError):
@@ -53,6 +53,10 @@ def load():
     lib.sbn_program_create_f64.argtypes = [i32, vp, i64, vp, i64, c.POINTER(vp)]
     lib.sbn_program_run_host_f64.restype = i32
     lib.sbn_program_run_host_f64.argtypes = [vp, vp, i64, i64, vp, i64]
+    lib.sbn_program_evidence_host.restype = i32
+    lib.sbn_program_evidence_host.argtypes = [vp, vp, i64, i64, vp]
+    lib.sbn_program_evidence_host_f64.restype = i32
+    lib.sbn_program_evidence_host_f64.argtypes = [vp, vp, i64, i64, vp]
     lib.sbn_program_destroy.restype = None
     lib.sbn_program_destroy.argtypes = [vp]
     lib.sbn_program_reserve.restype = i32
@@ -81,7 +85,7 @@ def load():
 
 EXPORTS = (
     "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_create_f64",
-    "sbn_program_run_host_f64", "sbn_program_destroy",
+    "sbn_program_run_host_f64", "sbn_program_evidence_host", "sbn_program_evidence_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
     "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_host_alloc", "sbn_host_free",
 )
@@ -200,6 +204,17 @@ class Program:
         ev_ptr = codes.ctypes.data if self.n_ev else None
         fn = load().sbn_program_run_host_f64 if self.f64 else load().sbn_program_run_host
         _check(fn(self._h, ev_ptr, n_rows, n_rows, out.ctypes.data, n_rows))
+        return out
+
+    def evidence(self, codes: np.ndarray, n_rows: int) -> np.ndarray:
+        """P(event) per evidence row (the normaliser of the posterior), host path."""
+        n_rows = int(n_rows)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if self.n_ev and codes.shape != (self.n_ev, n_rows):
+            raise ValueError(f"evidence codes have shape {codes.shape}, expected {(self.n_ev, n_rows)}")
+        out = np.empty(n_rows, dtype=np.float64 if self.f64 else np.float32)
+        fn = load().sbn_program_evidence_host_f64 if self.f64 else load().sbn_program_evidence_host
+        _check(fn(self._h, codes.ctypes.data if self.n_ev else None, n_rows, n_rows, out.ctypes.data))
         return out
 
     def run_device(self, d_ev: int, ld_ev: int, n_rows: int, d_out: int, ld_out: int, stream: int = 0):

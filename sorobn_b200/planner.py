@@ -246,7 +246,7 @@ def table_scale_log2(table: np.ndarray) -> int:
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
-               merge_sum_outs=None, lift_evidence=True) -> Plan:
+               merge_sum_outs=None, lift_evidence=True, allow_empty_query=False) -> Plan:
     """Plan P(query | evidence) for `net`.
 
     query / evidence are sequences of var ids.  `evidence` fixes the evidence
@@ -256,9 +256,11 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         merge_sum_outs = os.environ.get("SOROBN_B200_MERGE", "0") == "1"
     query = tuple(query)
     evidence = tuple(evidence)
-    if not query:
+    if not query and not allow_empty_query:
         # bayes_net.py:840-841
         raise ValueError("At least one query variable has to be specified")
+    if not query and not evidence:
+        raise ValueError("nothing to compute: no query variable and no evidence")
     if set(query) & set(evidence):
         # bayes_net.py:843-845
         raise ValueError("A query variable cannot be part of the event")

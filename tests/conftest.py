@@ -21,13 +21,15 @@ def load_golden(name):
         return json.load(f)
 
 
-def golden_names(kind=None):
+def golden_names(kinds=("example", "synthetic", "workload")):
+    """Golden files of the given kinds (query goldens by default; "predict_proba" for the
+    row-likelihood vectors)."""
     out = []
     for fn in sorted(os.listdir(GOLDEN)):
         if fn.endswith(".json"):
             with open(os.path.join(GOLDEN, fn)) as f:
                 g = json.load(f)
-            if kind is None or g["kind"] == kind:
+            if g["kind"] in kinds:
                 out.append(fn[:-5])
     return out
 

@@ -8,7 +8,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import build_network, case_event, dense_answer, golden_names, load_golden
+from conftest import build_network, case_event, dense_answer, golden_names, load_golden  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -432,3 +432,47 @@ def test_slab_variant_matches_plain_tile_walk():
             evd = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(evidence)}
             want = ve_oracle.query(dn, *query, event=evd, order=order)[1].reshape(-1)
             assert rel_err(with_slab[:, b], want) < RTOL
+
+
+@pytest.mark.parametrize("name", golden_names(kinds=("predict_proba",)))
+def test_predict_proba_matches_reference(name):
+    """Row likelihoods on the device (normaliser of an elimination with the row as evidence,
+    no query variable) against the reference's predict_proba on its example networks."""
+    from sorobn_b200 import examples
+
+    golden = load_golden(name)
+    bn = examples.build(examples.NETWORKS[golden["network"]])
+    worst = 0.0
+    for case in golden["cases"]:
+        X = pd.DataFrame(case["rows"], columns=case["columns"])
+        got = bn.predict_proba(X)
+        assert list(got.index.names) == sorted(case["columns"])
+        worst = max(worst, rel_err(got.to_numpy(), case["prob"]))
+        row = dict(zip(case["columns"], case["rows"][0]))
+        assert abs(bn.predict_proba(row) - case["prob"][0]) <= RTOL * case["prob"][0]
+    assert worst < RTOL, worst
+    # log-likelihood and the joint itself
+    X = pd.DataFrame(golden["cases"][0]["rows"], columns=golden["cases"][0]["columns"])
+    assert np.allclose(bn.predict_log_proba(X).to_numpy(), np.log(golden["cases"][0]["prob"]), rtol=1e-5, atol=1e-6)
+    fjd = bn.full_joint_dist()
+    assert np.isclose(fjd.sum(), 1.0) and len(fjd) == len(golden["cases"][0]["rows"])
+    assert np.allclose(np.sort(fjd.to_numpy()), np.sort(golden["cases"][0]["prob"]), rtol=1e-9)
+
+
+def test_predict_proba_order_and_zero_rows():
+    # reference test_predict_proba_order_doesnt_matter (test_bayes_net.py:340-354)
+    import itertools
+    import math
+
+    from sorobn_b200 import examples
+
+    bn = examples.alarm()
+    event = {"Alarm": False, "Burglary": False, "Earthquake": True, "John calls": False, "Mary calls": False}
+    base = bn.predict_proba(event)
+    for order in list(itertools.permutations(event))[:24]:
+        assert math.isclose(bn.predict_proba({v: event[v] for v in order}), base, rel_tol=1e-6)
+    # a combination the reference's joint does not contain (probability zero) gives 0.0
+    asia = examples.asia()
+    assert asia.predict_proba({"TB or cancer": False, "Lung cancer": True}) == 0.0
+    many = asia.predict_proba(pd.DataFrame({"TB or cancer": [False, True], "Lung cancer": [True, True]}))
+    assert many.iloc[0] == 0.0 and many.iloc[1] > 0

@@ -101,3 +101,23 @@ def test_query_argument_errors():
         ve_oracle.query(net, event={})
     with pytest.raises(ValueError):
         ve_oracle.query(net, "Alarm", event={"Alarm": True})
+
+
+@pytest.mark.parametrize("name", golden_names(kinds=("predict_proba",)))
+def test_evidence_probability_matches_reference_predict_proba(name):
+    """`predict_proba` of the REAL reference (bayes_net.py:934-962: full joint, marginalised and
+    looked up) against the oracle's P(event) and against a brute-force sum over the joint."""
+    from sorobn_b200 import examples
+
+    golden = load_golden(name)
+    bn = examples.build(examples.NETWORKS[golden["network"]])
+    net = oracle_net(bn)
+    joint = ve_oracle.full_joint(net)
+    for case in golden["cases"]:
+        cols = case["columns"]
+        for row, want in zip(case["rows"], case["prob"]):
+            ev = dict(zip(cols, row))
+            got = ve_oracle.evidence_probability(net, ev)
+            assert abs(got - want) <= 1e-12 * max(want, 1e-300), (ev, got, want)
+            idx = tuple(net.domains[v].index(ev[v]) if v in ev else slice(None) for v in joint.vars)
+            assert abs(joint.values[idx].sum() - want) <= 1e-12

@@ -229,3 +229,26 @@ def test_deferred_evidence_instantiation_keeps_answers_and_cuts_row_work():
         a = program_interp.run(lifted.words, lifted.table_blob64, codes)
         b = program_interp.run(direct.words, direct.table_blob64, codes)
         assert np.allclose(a, b, rtol=1e-12, atol=0)
+
+
+def test_programs_without_query_variables_give_the_evidence_probability():
+    """predict_proba path: no query variable, the normaliser is P(event)."""
+    bn = examples.asia()
+    net = bn._compiled
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    for ev_names in (["Smoker", "Dispnea"], ["Positive X-ray", "Visit to Asia", "Bronchitis"], list(bn.nodes)):
+        e = [net.index[v] for v in ev_names]
+        with pytest.raises(ValueError):
+            planner.build_plan(net, [], e)  # bayes_net.py:840 still holds for query()
+        plan = planner.build_plan(net, [], e, allow_empty_query=True)
+        assert plan.Q == 1
+        rng = np.random.default_rng(0)
+        codes = rng.integers(0, 2, size=(len(e), 9)).astype(np.uint8)
+        post, totals = program_interp.run(plan.words, plan.table_blob64, codes, return_totals=True)
+        for b in range(codes.shape[1]):
+            ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(ev_names)}
+            want = ve_oracle.evidence_probability(dn, ev)
+            assert abs(totals[b] - want) <= 1e-12 * max(want, 1e-300)
+            assert want == 0 or post[0, b] == 1.0
+    with pytest.raises(ValueError):
+        planner.build_plan(net, [], [], allow_empty_query=True)
