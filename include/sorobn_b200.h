@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 4
+#define SBN_ABI_VERSION 5
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -123,6 +123,22 @@ int sbn_program_set_graph(sbn_program *prog, int enabled);
  * preload schedule where available (default); 4 = tiled, x-loop schedule only; 5 = tiled
  * without the shared-memory slab variant for expanding products. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
+
+/* ------------------------------------------------------------------ Gibbs sampling
+ * `BayesNet._gibbs_sampling` (bayes_net.py:665-737) with one chain per evidence row.
+ * Variables are numbered topologically (every parent id < its child's id); CPT `v` lives at
+ * tables[cpt_off[v]] with axes [*parents(v), v], v fastest.  `query` lists the query
+ * variables slowest first (the order of the posterior's rows); `cycle` is the resampling
+ * order of the non-event variables (the reference: sorted by name).  out[q * ld_out + c] is
+ * the fraction of chain c's iterations spent in joint query state q. */
+typedef struct sbn_sampler sbn_sampler;
+int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int32_t *par_ptr, const int32_t *par_idx,
+                     const int32_t *cpt_off, const float *tables, int64_t n_table_floats, int32_t n_query,
+                     const int32_t *query, int32_t n_ev, const int32_t *ev_vars, int32_t n_cycle, const int32_t *cycle,
+                     sbn_sampler **out);
+int sbn_gibbs_run_host(sbn_sampler *sampler, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
+                       uint64_t seed, float *out, int64_t ld_out);
+void sbn_gibbs_destroy(sbn_sampler *sampler);
 
 /* Pinned host memory for evidence / posterior staging buffers. */
 int sbn_host_alloc(void **ptr, int64_t bytes);

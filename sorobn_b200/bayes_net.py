@@ -16,12 +16,14 @@ DataFrame); it is what the multi-GPU sharding and the benchmark drive.
 on the same kernels: the probability of a row is the normaliser of an elimination with the
 row as evidence.
 
-The sampling-based algorithms (gibbs / likelihood / rejection, bayes_net.py:577-737)
-and `fit` / `partial_fit` / `sample` are outside this path (scope table).
+`algorithm="gibbs"` (bayes_net.py:665-737) runs one chain per evidence row on the device
+(csrc/sbn_gibbs.cuh).  Likelihood weighting / rejection sampling (:577-663) and
+`fit` / `partial_fit` / `sample` are outside this round's scope (scope table).
 """
 from __future__ import annotations
 
 import graphlib
+import random
 import typing
 from collections import OrderedDict, defaultdict
 
@@ -47,6 +49,7 @@ class BayesNet:
     def __init__(self, *structure, prior_count: int = None, seed: int = None, device: int | None = None):
         self.prior_count = prior_count
         self.seed = seed
+        self._rng = random.Random(seed)  # seeds the device samplers (bayes_net.py:289)
         self.device = device
 
         parents = defaultdict(set)
@@ -233,8 +236,8 @@ class BayesNet:
             hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT)))
             self._engine_cache[key] = hit
             while len(self._engine_cache) > self.max_cached_programs:
-                _, (_, old) = self._engine_cache.popitem(last=False)
-                old.close()
+                _, old = self._engine_cache.popitem(last=False)
+                (old[1] if isinstance(old, tuple) else old).close()
         else:
             self._engine_cache.move_to_end(key)
         return hit
@@ -275,10 +278,15 @@ class BayesNet:
         for q in query:
             if q in event:
                 raise ValueError("A query variable cannot be part of the event")
+        if algorithm == "gibbs":
+            freq = self._gibbs(query, tuple(event), [[event[v]] for v in event], 1, n_iterations)
+            answer = pd.Series(freq[0][:, 0].astype(np.float64), index=freq[1],
+                               name=f"P({', '.join(map(str, query))})")
+            return answer[answer > 0]  # the reference only lists the states the chain visited
         if algorithm != "exact":
-            if algorithm in ("gibbs", "likelihood", "rejection"):
+            if algorithm in ("likelihood", "rejection"):
                 raise NotImplementedError(
-                    f"algorithm={algorithm!r} is outside the CUDA exact-inference path (see DESIGN.md)"
+                    f"algorithm={algorithm!r} is outside the CUDA path (exact and gibbs are implemented; DESIGN.md)"
                 )
             raise ValueError("Unknown algorithm, must be one of: exact, gibbs, likelihood, rejection")
 
@@ -295,7 +303,38 @@ class BayesNet:
             return answer.iloc[:0]
         return answer[post > 0]
 
-    def query_many(self, *query, events: pd.DataFrame, algorithm="exact") -> pd.DataFrame:
+    def _gibbs(self, query, ev_vars, columns, n_rows, n_iterations):
+        """One Gibbs chain per evidence row on the device (bayes_net.py:665-737): returns
+        (frequencies [Q, n_rows], answer index)."""
+        if self._compiled is None:
+            self._compile()
+            if self._compiled is None:
+                raise ValueError("every node needs a CPT in P before querying; call prepare()")
+        net = self._compiled
+        for name in (*query, *ev_vars):
+            if name not in net.index:
+                raise KeyError(name)
+        key = ("gibbs", tuple(query), tuple(ev_vars))
+        sampler = self._engine_cache.get(key)
+        q_sorted = sorted(query, key=str)
+        if sampler is None:
+            from . import engine
+
+            nonevents = sorted(set(self.nodes) - set(ev_vars))  # bayes_net.py:697, the cycle order
+            if not nonevents:
+                raise ValueError("every variable is observed: nothing to sample")
+            sampler = engine.GibbsSampler(net, [net.index[q] for q in q_sorted], [net.index[e] for e in ev_vars],
+                                          [net.index[v] for v in nonevents], device=self.device)
+            self._engine_cache[key] = sampler
+        codes, bad = self._encode_events(ev_vars, columns)
+        if bad.any():
+            raise ValueError("an event value is not a state of its variable")
+        freq = sampler.run(codes, n_rows, n_iterations, self._rng.getrandbits(63))
+        doms = [net.domains[net.index[q]] for q in q_sorted]
+        index = pd.Index(doms[0], name=q_sorted[0]) if len(q_sorted) == 1 else pd.MultiIndex.from_product(doms, names=q_sorted)
+        return freq, index
+
+    def query_many(self, *query, events: pd.DataFrame, algorithm="exact", n_iterations=100) -> pd.DataFrame:
         """Batched `query`: one posterior per row of `events` (columns = evidence
         variables).  Returns a DataFrame with one row per evidence row and one column
         per joint state of the query variables (same order as `query`'s index);
@@ -306,8 +345,12 @@ class BayesNet:
         for q in query:
             if q in ev_vars:
                 raise ValueError("A query variable cannot be part of the event")
+        if algorithm == "gibbs":
+            freq, index = self._gibbs(query, ev_vars, [events[v].to_numpy() for v in ev_vars], len(events.index),
+                                      n_iterations)
+            return pd.DataFrame(freq.T.astype(np.float64), index=events.index, columns=index)
         if algorithm != "exact":
-            raise NotImplementedError("query_many only implements algorithm='exact'")
+            raise NotImplementedError("query_many implements algorithm='exact' and 'gibbs'")
         plan, program = self._plan(query, ev_vars, _planner.MODE_BATCHED)
         n = len(events.index)
         if n == 0:

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libsorobn_b200.so")
 SOURCES = [os.path.join(HERE, "sbn_api.cu")]
-HEADERS = [os.path.join(HERE, "sbn_kernels.cuh"), os.path.join(os.path.dirname(PKG), "include", "sorobn_b200.h")]
+HEADERS = [os.path.join(HERE, "sbn_kernels.cuh"), os.path.join(HERE, "sbn_gibbs.cuh"), os.path.join(os.path.dirname(PKG), "include", "sorobn_b200.h")]
 
 
 def nvcc_path() -> str:

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "sbn_gibbs.cuh"
 #include "sbn_kernels.cuh"
 
 namespace {
@@ -1283,6 +1284,197 @@ int sbn_host_alloc(void **ptr, int64_t bytes) {
 
 int sbn_host_free(void *ptr) {
     if (ptr) SBN_CUDA(cudaFreeHost(ptr));
+    return SBN_OK;
+}
+
+}  // extern "C"
+
+// ================================================================== Gibbs sampling
+struct sbn_sampler {
+    int device = 0;
+    int n_vars = 0, n_query = 0, n_ev = 0, n_cycle = 0, Q = 0;
+    int32_t *d_ints = nullptr;  // one allocation for every int array
+    float *d_tables = nullptr;
+    const int32_t *card = nullptr, *cpt_off = nullptr, *par_ptr = nullptr, *par_idx = nullptr, *par_stride = nullptr,
+                  *chi_ptr = nullptr, *chi_idx = nullptr, *chi_stride = nullptr, *cycle = nullptr, *query = nullptr,
+                  *ev_var = nullptr;
+    uint8_t *d_ev = nullptr;
+    float *d_out = nullptr;
+    int64_t cap = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+};
+
+extern "C" {
+
+int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int32_t *par_ptr, const int32_t *par_idx,
+                     const int32_t *cpt_off, const float *tables, int64_t n_table_floats, int32_t n_query,
+                     const int32_t *query, int32_t n_ev, const int32_t *ev_vars, int32_t n_cycle, const int32_t *cycle,
+                     sbn_sampler **out) {
+    if (!card || !par_ptr || !cpt_off || !tables || !query || !cycle || !out || (n_ev > 0 && !ev_vars))
+        return fail(SBN_E_INVALID, "null argument");
+    *out = nullptr;
+    if (n_vars <= 0 || n_query <= 0 || n_cycle <= 0 || n_ev < 0) return fail(SBN_E_INVALID, "bad counts");
+    const int n_par = par_ptr[n_vars];
+    if (n_par > 0 && !par_idx) return fail(SBN_E_INVALID, "null parent list");
+    // parents precede children (ids are topological) and every CPT lies inside the blob
+    std::vector<int32_t> par_stride(n_par), chi_ptr(n_vars + 1, 0), chi_idx(n_par), chi_stride(n_par);
+    for (int v = 0; v < n_vars; ++v) {
+        if (card[v] < 1 || card[v] > SBN_GIBBS_MAX_CARD) return fail(SBN_E_INVALID, "variable %d has %d states (max %d)", v, card[v], SBN_GIBBS_MAX_CARD);
+        if (par_ptr[v] > par_ptr[v + 1]) return fail(SBN_E_INVALID, "bad parent CSR");
+        int64_t stride = card[v];
+        for (int k = par_ptr[v + 1] - 1; k >= par_ptr[v]; --k) {
+            const int pv = par_idx[k];
+            if (pv < 0 || pv >= v) return fail(SBN_E_INVALID, "variable ids must be topological (parent %d of %d)", pv, v);
+            par_stride[k] = static_cast<int32_t>(stride);
+            stride *= card[pv];
+            if (stride >= (1LL << 31)) return fail(SBN_E_INVALID, "CPT of variable %d is too large", v);
+            chi_ptr[pv + 1]++;
+        }
+        if (cpt_off[v] < 0 || cpt_off[v] + stride > n_table_floats) return fail(SBN_E_INVALID, "CPT %d outside the table blob", v);
+    }
+    for (int v = 0; v < n_vars; ++v) chi_ptr[v + 1] += chi_ptr[v];
+    {
+        std::vector<int32_t> fill(chi_ptr.begin(), chi_ptr.end() - 1);
+        for (int v = 0; v < n_vars; ++v)
+            for (int k = par_ptr[v]; k < par_ptr[v + 1]; ++k) {
+                const int pv = par_idx[k];
+                chi_idx[fill[pv]] = v;
+                chi_stride[fill[pv]] = par_stride[k];
+                fill[pv]++;
+            }
+    }
+    int64_t Q = 1;
+    for (int k = 0; k < n_query; ++k) {
+        if (query[k] < 0 || query[k] >= n_vars) return fail(SBN_E_INVALID, "query id out of range");
+        Q *= card[query[k]];
+        if (Q > 4096) return fail(SBN_E_INVALID, "more than 4096 joint query states");
+    }
+    for (int k = 0; k < n_ev; ++k)
+        if (ev_vars[k] < 0 || ev_vars[k] >= n_vars) return fail(SBN_E_INVALID, "evidence id out of range");
+    for (int k = 0; k < n_cycle; ++k)
+        if (cycle[k] < 0 || cycle[k] >= n_vars) return fail(SBN_E_INVALID, "cycle id out of range");
+    const size_t smem = ((static_cast<size_t>(n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(Q) * SBN_GIBBS_THREADS * 4;
+    if (smem > 200 * 1024) return fail(SBN_E_INVALID, "chain state needs %zu bytes of shared memory per CTA", smem);
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SBN_E_NODEVICE, "no CUDA device available");
+    if (device < 0 || device >= n_dev) return fail(SBN_E_NODEVICE, "device %d out of range", device);
+    sbn_sampler *S = new sbn_sampler();
+    S->device = device;
+    S->n_vars = n_vars;
+    S->n_query = n_query;
+    S->n_ev = n_ev;
+    S->n_cycle = n_cycle;
+    S->Q = static_cast<int>(Q);
+    auto bail = [&](int code) {
+        sbn_gibbs_destroy(S);
+        return code;
+    };
+#define SBN_CUDA_S(call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return bail(fail(SBN_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    SBN_CUDA_S(cudaSetDevice(device));
+    SBN_CUDA_S(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+    std::vector<int32_t> ints;
+    auto put = [&](const int32_t *src, size_t n) {
+        const size_t at = ints.size();
+        ints.insert(ints.end(), src, src + n);
+        return at;
+    };
+    const size_t o_card = put(card, n_vars), o_off = put(cpt_off, n_vars), o_pp = put(par_ptr, n_vars + 1),
+                 o_pi = put(par_idx ? par_idx : card, n_par), o_ps = put(par_stride.data(), n_par),
+                 o_cp = put(chi_ptr.data(), n_vars + 1), o_ci = put(chi_idx.data(), n_par),
+                 o_cs = put(chi_stride.data(), n_par), o_cy = put(cycle, n_cycle), o_q = put(query, n_query),
+                 o_ev = put(ev_vars ? ev_vars : card, n_ev);
+    SBN_CUDA_S(cudaMalloc(&S->d_ints, ints.size() * 4 + 4));
+    SBN_CUDA_S(cudaMemcpyAsync(S->d_ints, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice, S->stream));
+    SBN_CUDA_S(cudaMalloc(&S->d_tables, static_cast<size_t>(n_table_floats) * 4));
+    SBN_CUDA_S(cudaMemcpyAsync(S->d_tables, tables, static_cast<size_t>(n_table_floats) * 4, cudaMemcpyHostToDevice, S->stream));
+    SBN_CUDA_S(cudaStreamSynchronize(S->stream));
+    S->card = S->d_ints + o_card;
+    S->cpt_off = S->d_ints + o_off;
+    S->par_ptr = S->d_ints + o_pp;
+    S->par_idx = S->d_ints + o_pi;
+    S->par_stride = S->d_ints + o_ps;
+    S->chi_ptr = S->d_ints + o_cp;
+    S->chi_idx = S->d_ints + o_ci;
+    S->chi_stride = S->d_ints + o_cs;
+    S->cycle = S->d_ints + o_cy;
+    S->query = S->d_ints + o_q;
+    S->ev_var = S->d_ints + o_ev;
+    SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#undef SBN_CUDA_S
+    *out = S;
+    return SBN_OK;
+}
+
+void sbn_gibbs_destroy(sbn_sampler *S) {
+    if (!S) return;
+    cudaSetDevice(S->device);
+    cudaFree(S->d_ints);
+    cudaFree(S->d_tables);
+    cudaFree(S->d_ev);
+    cudaFree(S->d_out);
+    if (S->stream) cudaStreamDestroy(S->stream);
+    delete S;
+}
+
+int sbn_gibbs_run_host(sbn_sampler *S, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
+                       uint64_t seed, float *out, int64_t ld_out) {
+    if (!S || !out) return fail(SBN_E_INVALID, "null argument");
+    if (n_chains <= 0 || n_iterations <= 0) return fail(SBN_E_INVALID, "n_chains and n_iterations must be positive");
+    if (S->n_ev > 0 && (!ev || (S->n_ev > 1 && ld_ev < n_chains))) return fail(SBN_E_INVALID, "bad evidence");
+    if (S->Q > 1 && ld_out < n_chains) return fail(SBN_E_INVALID, "ld_out < n_chains");
+    SBN_CUDA(cudaSetDevice(S->device));
+    if (n_chains > S->cap) {
+        cudaFree(S->d_ev);
+        cudaFree(S->d_out);
+        S->d_ev = nullptr;
+        S->d_out = nullptr;
+        if (S->n_ev > 0) SBN_CUDA(cudaMalloc(&S->d_ev, static_cast<size_t>(S->n_ev) * n_chains));
+        SBN_CUDA(cudaMalloc(&S->d_out, static_cast<size_t>(S->Q) * n_chains * 4));
+        S->cap = n_chains;
+    }
+    if (S->n_ev > 0)
+        SBN_CUDA(cudaMemcpy2DAsync(S->d_ev, static_cast<size_t>(n_chains), ev, static_cast<size_t>(ld_ev),
+                                   static_cast<size_t>(n_chains), static_cast<size_t>(S->n_ev), cudaMemcpyHostToDevice, S->stream));
+    SbnGibbs g;
+    memset(&g, 0, sizeof g);
+    g.n_vars = S->n_vars;
+    g.n_cycle = S->n_cycle;
+    g.n_query = S->n_query;
+    g.Q = S->Q;
+    g.n_ev = S->n_ev;
+    g.card = S->card;
+    g.cpt_off = S->cpt_off;
+    g.par_ptr = S->par_ptr;
+    g.par_idx = S->par_idx;
+    g.par_stride = S->par_stride;
+    g.chi_ptr = S->chi_ptr;
+    g.chi_idx = S->chi_idx;
+    g.chi_stride = S->chi_stride;
+    g.cycle = S->cycle;
+    g.query = S->query;
+    g.ev_var = S->ev_var;
+    g.tables = S->d_tables;
+    g.ev = S->d_ev;
+    g.ld_ev = n_chains;
+    g.out = S->d_out;
+    g.ld_out = n_chains;
+    g.n_chains = n_chains;
+    g.n_iterations = n_iterations;
+    g.seed = seed;
+    const size_t smem = ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(S->Q) * SBN_GIBBS_THREADS * 4;
+    const int64_t grid = (n_chains + SBN_GIBBS_THREADS - 1) / SBN_GIBBS_THREADS;
+    sbn_gibbs_kernel<<<static_cast<unsigned>(grid), SBN_GIBBS_THREADS, smem, S->stream>>>(g);
+    SBN_CUDA(cudaGetLastError());
+    S->launches++;
+    SBN_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(ld_out) * 4, S->d_out, static_cast<size_t>(n_chains) * 4,
+                               static_cast<size_t>(n_chains) * 4, static_cast<size_t>(S->Q), cudaMemcpyDeviceToHost, S->stream));
+    SBN_CUDA(cudaStreamSynchronize(S->stream));
     return SBN_OK;
 }
 

@@ -1,0 +1,172 @@
+// sorobn_b200 -- Gibbs sampling on the device (BASELINE.json configs[4]).
+//
+// Mirrors `BayesNet._gibbs_sampling` (/root/reference/sorobn/bayes_net.py:665-737):
+//   * start from a forward sample with the event variables clamped (bayes_net.py:715,
+//     `self.sample(init=event)` -> `_forward_sample`, :518-548);
+//   * every iteration takes the next non-event variable in a fixed cycle (sorted by name,
+//     :697 and :718) and resamples it from P(var | Markov blanket) (:724-729);
+//   * after every iteration the current state of the query variables is recorded (:732-733);
+//   * the answer is the frequency of each joint query state (:736-737).
+// The reference precomputes one table per variable over its whole Markov boundary with pandas
+// (:699-712); here the conditional is evaluated on the fly, which needs only the CPT of the
+// variable and of its children:
+//     P(v = x | blanket)  ~  P(x | pa(v)) * prod_{c in children(v)} P(c | pa(c) with v = x)
+// One thread runs one chain (one evidence row); 128 chains per CTA with their states in
+// shared memory ([variable][chain], conflict-free), CPTs read through L1.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SBN_GIBBS_THREADS 128
+#define SBN_GIBBS_MAX_CARD 64
+
+struct SbnGibbs {
+    int32_t n_vars;
+    int32_t n_cycle;             // non-event variables
+    int32_t n_query;
+    int32_t Q;                   // joint query states
+    int32_t n_ev;
+    int32_t pad_;
+    const int32_t *card;         // [n_vars]
+    const int32_t *cpt_off;      // [n_vars] float offset of each CPT (axes [*parents, var], var fastest)
+    const int32_t *par_ptr;      // [n_vars + 1] CSR of parents
+    const int32_t *par_idx;      //   parent ids
+    const int32_t *par_stride;   //   stride of that parent in the child's CPT
+    const int32_t *chi_ptr;      // [n_vars + 1] CSR of children
+    const int32_t *chi_idx;      //   child ids
+    const int32_t *chi_stride;   //   stride of the variable inside that child's CPT
+    const int32_t *cycle;        // [n_cycle] variable ids in cycle order
+    const int32_t *query;        // [n_query] query variable ids, slowest first
+    const int32_t *ev_var;       // [n_ev] evidence variable ids (column order of `ev`)
+    const float *tables;
+    const uint8_t *ev;           // [n_ev][ld_ev] state codes
+    int64_t ld_ev;
+    float *out;                  // [Q][ld_out] frequencies
+    int64_t ld_out;
+    int64_t n_chains;
+    int64_t n_iterations;
+    uint64_t seed;
+};
+
+// Philox-4x32-10 (Salmon et al. 2011): counter-based, so chain c / draw k is reproducible.
+__device__ __forceinline__ void sbn_philox(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n2 = hi0 ^ ctr[3] ^ k1;
+        ctr[0] = n0;
+        ctr[1] = lo1;
+        ctr[2] = n2;
+        ctr[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+struct SbnRng {
+    uint32_t buf[4];
+    uint32_t k0, k1, chain_lo, chain_hi;
+    uint32_t counter;
+    int have;
+    __device__ void init(uint64_t seed, uint64_t chain) {
+        k0 = static_cast<uint32_t>(seed);
+        k1 = static_cast<uint32_t>(seed >> 32);
+        chain_lo = static_cast<uint32_t>(chain);
+        chain_hi = static_cast<uint32_t>(chain >> 32);
+        counter = 0;
+        have = 0;
+    }
+    __device__ float uniform() {  // (0, 1]
+        if (have == 0) {
+            buf[0] = counter++;
+            buf[1] = 0;
+            buf[2] = chain_lo;
+            buf[3] = chain_hi;
+            sbn_philox(buf, k0, k1);
+            have = 4;
+        }
+        const uint32_t u = buf[--have];
+        return (static_cast<float>(u >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    }
+};
+
+__global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_gibbs_kernel(const __grid_constant__ SbnGibbs p) {
+    extern __shared__ uint8_t s_raw[];
+    // layout: state [n_vars][T] bytes, then counts [Q][T] uint32 (4-byte aligned)
+    uint8_t *state = s_raw + threadIdx.x;
+    const int T = SBN_GIBBS_THREADS;
+    uint32_t *counts = reinterpret_cast<uint32_t *>(s_raw + ((static_cast<size_t>(p.n_vars) * T + 15) / 16) * 16) + threadIdx.x;
+
+    const int64_t chain = static_cast<int64_t>(blockIdx.x) * T + threadIdx.x;
+    if (chain >= p.n_chains) return;
+    SbnRng rng;
+    rng.init(p.seed, static_cast<uint64_t>(chain));
+    for (int q = 0; q < p.Q; ++q) counts[q * T] = 0;
+
+    // ---- initial state: forward sample, event variables clamped (bayes_net.py:518-548)
+    for (int v = 0; v < p.n_vars; ++v) state[v * T] = 0xff;
+    for (int k = 0; k < p.n_ev; ++k) {
+        const int v = p.ev_var[k];
+        state[v * T] = min(static_cast<int>(p.ev[static_cast<int64_t>(k) * p.ld_ev + chain]), p.card[v] - 1);
+    }
+    for (int v = 0; v < p.n_vars; ++v) {  // variable ids are topological
+        if (state[v * T] != 0xff) continue;
+        int base = p.cpt_off[v];
+        for (int k = p.par_ptr[v]; k < p.par_ptr[v + 1]; ++k) base += state[p.par_idx[k] * T] * p.par_stride[k];
+        const int c = p.card[v];
+        float u = rng.uniform(), acc = 0.f;
+        int pick = c - 1;
+        for (int x = 0; x < c; ++x) {
+            acc += __ldg(p.tables + base + x);
+            if (u <= acc) {
+                pick = x;
+                break;
+            }
+        }
+        state[v * T] = static_cast<uint8_t>(pick);
+    }
+
+    // ---- the chain
+    int cyc = 0;
+    for (int64_t it = 0; it < p.n_iterations; ++it) {
+        const int v = p.cycle[cyc];
+        cyc = cyc + 1 == p.n_cycle ? 0 : cyc + 1;
+        const int c = p.card[v];
+        float w[SBN_GIBBS_MAX_CARD];
+        int base = p.cpt_off[v];
+        for (int k = p.par_ptr[v]; k < p.par_ptr[v + 1]; ++k) base += state[p.par_idx[k] * T] * p.par_stride[k];
+        for (int x = 0; x < c; ++x) w[x] = __ldg(p.tables + base + x);
+        for (int k = p.chi_ptr[v]; k < p.chi_ptr[v + 1]; ++k) {
+            const int ch = p.chi_idx[k];
+            const int sv = p.chi_stride[k];
+            int cb = p.cpt_off[ch] + state[ch * T];  // the child's own axis has stride 1
+            for (int j = p.par_ptr[ch]; j < p.par_ptr[ch + 1]; ++j) {
+                const int pj = p.par_idx[j];
+                if (pj != v) cb += state[pj * T] * p.par_stride[j];
+            }
+            for (int x = 0; x < c; ++x) w[x] *= __ldg(p.tables + cb + x * sv);
+        }
+        float total = 0.f;
+        for (int x = 0; x < c; ++x) total += w[x];
+        if (total > 0.f) {  // an all-zero conditional (deterministic CPTs) keeps the current value
+            const float u = rng.uniform() * total;
+            float acc = 0.f;
+            int pick = c - 1;
+            for (int x = 0; x < c; ++x) {
+                acc += w[x];
+                if (u <= acc) {
+                    pick = x;
+                    break;
+                }
+            }
+            state[v * T] = static_cast<uint8_t>(pick);
+        }
+        // record the joint state of the query variables (bayes_net.py:732-733)
+        int qi = 0;
+        for (int k = 0; k < p.n_query; ++k) qi = qi * p.card[p.query[k]] + state[p.query[k] * T];
+        counts[qi * T] += 1;
+    }
+    const float inv = 1.0f / static_cast<float>(p.n_iterations);
+    for (int q = 0; q < p.Q; ++q) p.out[static_cast<int64_t>(q) * p.ld_out + chain] = static_cast<float>(counts[q * T]) * inv;
+}

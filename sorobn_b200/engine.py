@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class EngineError(RuntimeError):
@@ -73,6 +73,12 @@ def load():
     lib.sbn_program_set_graph.argtypes = [vp, i32]
     lib.sbn_program_set_tiled.restype = i32
     lib.sbn_program_set_tiled.argtypes = [vp, i32]
+    lib.sbn_gibbs_create.restype = i32
+    lib.sbn_gibbs_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, i32, vp, c.POINTER(vp)]
+    lib.sbn_gibbs_run_host.restype = i32
+    lib.sbn_gibbs_run_host.argtypes = [vp, vp, i64, i64, i64, c.c_uint64, vp, i64]
+    lib.sbn_gibbs_destroy.restype = None
+    lib.sbn_gibbs_destroy.argtypes = [vp]
     lib.sbn_host_alloc.restype = i32
     lib.sbn_host_alloc.argtypes = [c.POINTER(vp), i64]
     lib.sbn_host_free.restype = i32
@@ -87,7 +93,8 @@ EXPORTS = (
     "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_create_f64",
     "sbn_program_run_host_f64", "sbn_program_evidence_host", "sbn_program_evidence_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
-    "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_host_alloc", "sbn_host_free",
+    "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_gibbs_create", "sbn_gibbs_run_host",
+    "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
 )
 
 
@@ -229,3 +236,61 @@ class Program:
                                           ctypes.c_void_p(d_out), int(ld_out), ctypes.c_void_p(stream),
                                           ms.ctypes.data, n))
         return ms
+
+
+class GibbsSampler:
+    """Device Gibbs sampler for one (query variables, evidence variables) pair: one chain per
+    evidence row (csrc/sbn_gibbs.cuh; the reference: bayes_net.py:665-737)."""
+
+    def __init__(self, net, query_ids, evidence_ids, cycle_ids, device: int | None = None):
+        lib = load()
+        self.device = default_device() if device is None else int(device)
+        n = len(net.names)
+        card = np.ascontiguousarray(net.card, dtype=np.int32)
+        par_ptr = np.zeros(n + 1, dtype=np.int32)
+        par_idx = []
+        offsets = np.zeros(n, dtype=np.int32)
+        blob = []
+        off = 0
+        for v in range(n):
+            par_idx.extend(net.parents[v])
+            par_ptr[v + 1] = len(par_idx)
+            t = np.ascontiguousarray(net.cpt[v], dtype=np.float32).reshape(-1)
+            offsets[v] = off
+            blob.append(t)
+            off += t.size
+        self._tables = np.concatenate(blob)
+        par_idx = np.ascontiguousarray(par_idx, dtype=np.int32)
+        self.query = np.ascontiguousarray(query_ids, dtype=np.int32)
+        self.evidence = np.ascontiguousarray(evidence_ids, dtype=np.int32)
+        cycle = np.ascontiguousarray(cycle_ids, dtype=np.int32)
+        self.Q = int(np.prod([net.card[q] for q in query_ids]))
+        self.n_ev = len(evidence_ids)
+        self._h = ctypes.c_void_p()
+        _check(lib.sbn_gibbs_create(
+            self.device, n, card.ctypes.data, par_ptr.ctypes.data, par_idx.ctypes.data if par_idx.size else None,
+            offsets.ctypes.data, self._tables.ctypes.data, self._tables.size, len(self.query), self.query.ctypes.data,
+            self.n_ev, self.evidence.ctypes.data if self.n_ev else None, len(cycle), cycle.ctypes.data,
+            ctypes.byref(self._h)))
+
+    def run(self, codes: np.ndarray, n_chains: int, n_iterations: int, seed: int) -> np.ndarray:
+        """uint8 codes [n_ev, n_chains] -> frequencies float32 [Q, n_chains]."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if self.n_ev and codes.shape != (self.n_ev, n_chains):
+            raise ValueError(f"evidence codes have shape {codes.shape}, expected {(self.n_ev, n_chains)}")
+        out = np.empty((self.Q, n_chains), dtype=np.float32)
+        _check(load().sbn_gibbs_run_host(self._h, codes.ctypes.data if self.n_ev else None, n_chains, n_chains,
+                                         int(n_iterations), ctypes.c_uint64(int(seed) & (2**64 - 1)), out.ctypes.data,
+                                         n_chains))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load().sbn_gibbs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -138,7 +138,9 @@ def test_query_argument_errors_do_not_need_a_gpu():
     with pytest.raises(ValueError, match="Unknown algorithm"):
         bn.query("Alarm", event={}, algorithm="magic")
     with pytest.raises(NotImplementedError):
-        bn.query("Alarm", event={}, algorithm="gibbs")
+        bn.query("Alarm", event={}, algorithm="likelihood")
+    with pytest.raises(NotImplementedError):
+        bn.query("Alarm", event={}, algorithm="rejection")
 
 
 def test_no_silent_cpu_fallback():
@@ -150,6 +152,10 @@ def test_no_silent_cpu_fallback():
         bn.query("Burglary", event={"John calls": True, "Mary calls": True})
     with pytest.raises(engine.EngineError):
         bn.query_many("Burglary", events=pd.DataFrame({"John calls": [True], "Mary calls": [False]}))
+    with pytest.raises(engine.EngineError):
+        bn.query("Burglary", event={"John calls": True}, algorithm="gibbs", n_iterations=10)
+    with pytest.raises(engine.EngineError):
+        bn.predict_proba({"John calls": True, "Mary calls": False})
 
 
 def test_library_loads_and_exports_every_declared_symbol():
