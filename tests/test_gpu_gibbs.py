@@ -53,7 +53,7 @@ def test_one_chain_per_evidence_row_matches_exact_batch():
     B = 512
     events = synthetic.random_events(spec, evidence, B, seed=5)
     exact = bn.query_many(*query, events=events).to_numpy()
-    gibbs = bn.query_many(*query, events=events, algorithm="gibbs", n_iterations=30_000).to_numpy()
+    gibbs = bn.query_many(*query, events=events, algorithm="gibbs", n_iterations=120_000).to_numpy()
     assert gibbs.shape == exact.shape
     assert np.allclose(gibbs.sum(axis=1), 1.0, atol=1e-5)
     err = np.abs(gibbs - exact)
