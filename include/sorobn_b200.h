@@ -69,8 +69,9 @@ int sbn_program_create(int device, const int32_t *words, int64_t n_words, const 
                        int64_t n_table_floats, sbn_program **out);
 void sbn_program_destroy(sbn_program *prog);
 
-/* Same for a single-event ("flat", mode 0) program evaluated in float64: tables, scratch
- * and the posterior are doubles.  One query is launch-latency bound, so it gets the
+/* Same for a program evaluated in float64: tables, scratch and the posterior are doubles.
+ * Single-event ("flat", mode 0) programs are what `BayesNet.query` uses; batched ones re-run
+ * the rows a float32 program flagged.  One query is launch-latency bound, so it gets the
  * reference's own precision and range (float64, bayes_net.py throughout) for free; it is
  * also the fallback for evidence rows too unlikely for float32 (see run_host below). */
 int sbn_program_create_f64(int device, const int32_t *words, int64_t n_words, const double *tables,
@@ -86,7 +87,8 @@ int sbn_program_reserve(sbn_program *prog, int64_t max_rows);
 int sbn_program_run_host(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, float *out,
                          int64_t ld_out);
 
-/* float64 programs (n_rows must be 1). */
+/* float64 programs: flat (n_rows must be 1) or batched (the robust fallback for rows that
+ * the float32 program flagged; plain kernel in double, several times slower). */
 int sbn_program_run_host_f64(sbn_program *prog, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, double *out,
                              int64_t ld_out);
 

@@ -216,13 +216,13 @@ class BayesNet:
         self._engine_cache = OrderedDict()
 
     # ---------------------------------------------------------------------- query
-    def _plan(self, query, evidence_vars, mode):
+    def _plan(self, query, evidence_vars, mode, robust=False):
         if self._compiled is None:
             self._compile()
             if self._compiled is None:
                 raise ValueError("every node needs a CPT in P before querying; call prepare()")
         net = self._compiled
-        key = (tuple(query), tuple(evidence_vars), mode)
+        key = (tuple(query), tuple(evidence_vars), mode, robust)
         hit = self._engine_cache.get(key)
         if hit is None:
             for name in (*query, *evidence_vars):
@@ -232,8 +232,9 @@ class BayesNet:
                                        mode=mode, allow_empty_query=True)
             from . import engine  # raises if libsorobn_b200.so cannot be loaded
 
-            # single-event programs run in float64 (latency-bound anyway); batches in float32
-            hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT)))
+            # single-event programs run in float64 (latency-bound anyway); batches in float32,
+            # except the robust re-run of flagged rows (mode key "batched64")
+            hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT or robust)))
             self._engine_cache[key] = hit
             while len(self._engine_cache) > self.max_cached_programs:
                 _, old = self._engine_cache.popitem(last=False)
@@ -362,9 +363,13 @@ class BayesNet:
         # NaN rows: impossible evidence, or a normaliser so small that float32 may have
         # underflowed -- settle those one by one with the float64 single-event program
         suspect = np.isnan(post).any(axis=0) & ~bad
-        if suspect.any():
+        rows = np.nonzero(suspect)[0]
+        if len(rows) > 8:  # many rows below the float32 range: one batched float64 run
+            _, robust = self._plan(query, ev_vars, _planner.MODE_BATCHED, robust=True)
+            post[:, rows] = robust.run(np.ascontiguousarray(codes[:, rows]), len(rows))
+        elif len(rows):
             _, flat = self._plan(query, ev_vars, _planner.MODE_FLAT)
-            for b in np.nonzero(suspect)[0]:
+            for b in rows:
                 post[:, b] = flat.run(np.ascontiguousarray(codes[:, b:b + 1]), 1)[:, 0]
         out = pd.DataFrame(post.T, index=events.index, columns=self._answer_index(plan))
         if bad.any():
@@ -406,10 +411,13 @@ class BayesNet:
         plan, program = self._plan((), ev_vars, _planner.MODE_BATCHED)
         codes, bad = self._encode_events(ev_vars, [X[v].to_numpy() for v in ev_vars])
         prob = program.evidence(codes, n).astype(np.float64)
-        suspect = np.isnan(prob) & ~bad
-        if suspect.any():  # below the float32 range (or exactly zero): settle in float64
+        rows = np.nonzero(np.isnan(prob) & ~bad)[0]
+        if len(rows) > 8:  # below the float32 range (or exactly zero): settle in float64
+            _, robust = self._plan((), ev_vars, _planner.MODE_BATCHED, robust=True)
+            prob[rows] = robust.evidence(np.ascontiguousarray(codes[:, rows]), len(rows))
+        elif len(rows):
             _, flat = self._plan((), ev_vars, _planner.MODE_FLAT)
-            for b in np.nonzero(suspect)[0]:
+            for b in rows:
                 prob[b] = flat.evidence(np.ascontiguousarray(codes[:, b:b + 1]), 1)[0]
         prob[np.isnan(prob) | bad] = 0.0
         return pd.Series(prob, index=index, name=name)

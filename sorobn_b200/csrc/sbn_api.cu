@@ -528,11 +528,11 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     q->n_axes = static_cast<int32_t>(st.cards.size());
     q->cx = st.cx;
     q->zoff = st.zoff_pos >= 0 ? P->d_tile_off + st.zoff_pos : nullptr;
-    if (st.kind == 1 && st.tile > 0 && P->use_tiled && st.zoff_tiled_pos >= 0) q->zoff = P->d_tile_off + st.zoff_tiled_pos;
+    if (st.kind == 1 && st.tile > 0 && P->use_tiled && !P->f64 && st.zoff_tiled_pos >= 0) q->zoff = P->d_tile_off + st.zoff_tiled_pos;
     q->n_out = static_cast<int32_t>(st.n_out);
     for (size_t j = 0; j < st.cards.size(); ++j) q->card[j] = st.cards[j];
     int smem = 0;
-    const bool tiled = st.kind == 1 && st.tile > 0 && P->use_tiled;
+    const bool tiled = st.kind == 1 && st.tile > 0 && P->use_tiled && !P->f64;
     for (size_t i = 0; i < st.in.size(); ++i) {
         const InDesc &in = st.in[tiled ? st.order[i] : i];
         SbnInput &d = q->in[i];
@@ -558,7 +558,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
                 ((in.strides.size() > 1 && in.strides[1] != 0) ? 2 : 0);
         d.smem_off = -1;
         d.stage_floats = 0;
-        if (st.kind == 1 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
+        if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
             d.smem_off = smem;
             d.stage_floats = static_cast<int32_t>(padded);
             smem += static_cast<int>(padded);
@@ -598,7 +598,8 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     } else if (st.kind == 1) {
         const int c0 = q->n_axes > 0 ? q->card[0] : 1;
         const int c1 = q->n_axes > 1 ? q->card[1] : 1;
-        const int64_t n_bblocks = (n_rows + SBN_ROWS_PER_CTA - 1) / SBN_ROWS_PER_CTA;
+        const int64_t rows_per_cta = P->f64 ? SBN_THREADS * 2 : SBN_ROWS_PER_CTA;  // double2 / float4 per thread
+        const int64_t n_bblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
         const int64_t rest = st.n_out / (static_cast<int64_t>(c0) * c1);
         // Tile = axis 0 x tile1 digits of axis 1.  Start from ~32 outputs per thread and
         // shrink while the grid is below two full waves (148 SMs x 16 CTAs).
@@ -791,6 +792,21 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
     const int64_t rest = st.n_out / (static_cast<int64_t>(q.n_axes > 0 ? q.card[0] : 1) * (q.n_axes > 1 ? q.card[1] : 1));
     const int64_t grid = static_cast<int64_t>(q.n_bblocks) * q.n_tile1 * rest;
     if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
+    if (P->f64) {
+        const dim3 g(static_cast<unsigned>(grid)), b(SBN_THREADS);
+        switch (q.n_in) {
+            case 1: sbn_step_batched_f64<1><<<g, b, 0, stream>>>(q); break;
+            case 2: sbn_step_batched_f64<2><<<g, b, 0, stream>>>(q); break;
+            case 3: sbn_step_batched_f64<3><<<g, b, 0, stream>>>(q); break;
+            case 4: sbn_step_batched_f64<4><<<g, b, 0, stream>>>(q); break;
+            case 5: sbn_step_batched_f64<5><<<g, b, 0, stream>>>(q); break;
+            case 6: sbn_step_batched_f64<6><<<g, b, 0, stream>>>(q); break;
+            case 7: sbn_step_batched_f64<7><<<g, b, 0, stream>>>(q); break;
+            case 8: sbn_step_batched_f64<8><<<g, b, 0, stream>>>(q); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     switch (q.n_in) {
         case 1: return launch_batched_n<1>(q, grid, stream);
         case 2: return launch_batched_n<2>(q, grid, stream);
@@ -941,7 +957,7 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
     P->f64 = f64;
     const size_t elem = f64 ? 8 : 4;
     int rc = parse(P, words, n_words);
-    if (rc == SBN_OK && f64 && P->mode != 0) rc = fail(SBN_E_INVALID, "float64 programs must be flat (single event)");
+
     if (rc != SBN_OK) {
         delete P;
         return rc;
@@ -1069,7 +1085,8 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
     SBN_CUDA(cudaSetDevice(P->device));
     SBN_CUDA(cudaStreamSynchronize(P->stream));
     free_scratch(P);
-    const int64_t per_row = batched_floats_per_row(P) * 4 + P->n_ev + static_cast<int64_t>(P->Q) * 4;
+    const int64_t elem = P->f64 ? 8 : 4;
+    const int64_t per_row = batched_floats_per_row(P) * elem + P->n_ev + static_cast<int64_t>(P->Q) * elem + elem;
     size_t free_b = 0, total_b = 0;
     SBN_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const int64_t budget = static_cast<int64_t>(free_b * 0.85);
@@ -1081,16 +1098,16 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
     const int64_t ld = round_up(rows, 32);
     const int64_t arena = batched_floats_per_row(P) * ld;
     if (arena > 0) {
-        cudaError_t e = cudaMalloc(&P->d_arena, static_cast<size_t>(arena) * 4);
+        cudaError_t e = cudaMalloc(&P->d_arena, static_cast<size_t>(arena) * elem);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            return fail(SBN_E_NOMEM, "cudaMalloc of %lld scratch bytes failed: %s", (long long)arena * 4,
+            return fail(SBN_E_NOMEM, "cudaMalloc of %lld scratch bytes failed: %s", (long long)(arena * elem),
                         cudaGetErrorString(e));
         }
         int64_t off = 0;
         for (Slot &s : P->slots)
             if (s.batched) {
-                s.ptr = P->d_arena + off;
+                s.ptr = reinterpret_cast<float *>(reinterpret_cast<char *>(P->d_arena) + off * elem);
                 off += s.size * ld;
             }
     }

@@ -239,6 +239,77 @@ __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_con
 }
 
 
+// --------------------------------------------------- batched step kernel, float64
+// The robust fallback for evidence rows below the float32 range (SBN_MIN_TOTAL_F32): same
+// contract and grid as sbn_step_batched, scalars are double (tables, scratch and output),
+// 2 rows per thread (one 128-bit load), tables read through L1 (no staging).
+template <int N_IN>
+__global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched_f64(const __grid_constant__ SbnStep p) {
+    const int bblock = blockIdx.x % p.n_bblocks;
+    int r = blockIdx.x / p.n_bblocks;  // tile id
+    const int b = (bblock * SBN_THREADS + threadIdx.x) * 2;
+    if (b >= p.n_rows) return;
+    const int c0 = p.n_axes > 0 ? p.card[0] : 1;
+    const int c1 = p.n_axes > 1 ? p.card[1] : 1;
+    const int t1 = r % p.n_tile1;
+    r /= p.n_tile1;
+    const int d1_begin = t1 * p.tile1;
+    const int d1_end = min(c1, d1_begin + p.tile1);
+    const int o_rest = r * c0 * c1;
+    int off[N_IN];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) off[i] = 0;
+    for (int j = 2; j < p.n_axes; ++j) {
+        const int c = p.card[j];
+        const int d = r % c;
+        r /= c;
+#pragma unroll
+        for (int i = 0; i < N_IN; ++i) off[i] += d * p.in[i].stride[j];
+    }
+    int evo[N_IN][2];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) {
+        evo[i][0] = evo[i][1] = 0;
+        if (!p.in[i].batched) {
+            for (int k = 0; k < p.in[i].n_ev; ++k) {
+                const uint8_t *col = p.ev + static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev + b;
+                const int s = p.in[i].ev_stride[k];
+                const int top = p.in[i].ev_card[k] - 1;
+#pragma unroll
+                for (int l = 0; l < 2; ++l) evo[i][l] += ((b + l < p.n_rows) ? min(static_cast<int>(col[l]), top) : 0) * s;
+            }
+        }
+    }
+    const int64_t ld = p.ld;
+    double *const out = reinterpret_cast<double *>(p.out);
+    for (int d1 = d1_begin; d1 < d1_end; ++d1) {
+        for (int d0 = 0; d0 < c0; ++d0) {
+            double a0 = 0.0, a1 = 0.0;
+            for (int x = 0; x < p.cx; ++x) {
+                double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+                for (int i = 0; i < N_IN; ++i) {
+                    const int e = off[i] + d0 * (p.n_axes > 0 ? p.in[i].stride[0] : 0) +
+                                  d1 * (p.n_axes > 1 ? p.in[i].stride[1] : 0) +
+                                  (p.zoff ? __ldg(p.zoff + i * p.cx + x) : x * p.in[i].sx);
+                    const double *src = reinterpret_cast<const double *>(p.in[i].ptr);
+                    if (p.in[i].batched) {
+                        const double2 v = *reinterpret_cast<const double2 *>(src + static_cast<int64_t>(e) * ld + b);
+                        p0 *= v.x;
+                        p1 *= v.y;
+                    } else {
+                        p0 *= __ldg(src + e + evo[i][0]);
+                        p1 *= __ldg(src + e + evo[i][1]);
+                    }
+                }
+                a0 += p0;
+                a1 += p1;
+            }
+            *reinterpret_cast<double2 *>(out + static_cast<int64_t>(o_rest + d1 * c0 + d0) * ld + b) = make_double2(a0, a1);
+        }
+    }
+}
+
 // --------------------------------------------------------------- tiled step kernel
 // The fast path.  Same contract as sbn_step_batched, different blocking:
 //

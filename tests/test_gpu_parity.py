@@ -476,3 +476,39 @@ def test_predict_proba_order_and_zero_rows():
     assert asia.predict_proba({"TB or cancer": False, "Lung cancer": True}) == 0.0
     many = asia.predict_proba(pd.DataFrame({"TB or cancer": [False, True], "Lung cancer": [True, True]}))
     assert many.iloc[0] == 0.0 and many.iloc[1] > 0
+
+
+def test_batch_of_unlikely_rows_goes_through_the_batched_float64_program():
+    """Most variables observed on a 60-node chain: every row has P(event) around 1e-40..1e-60,
+    below the float32 threshold, so query_many / predict_proba re-run the whole batch with the
+    batched float64 program (plain kernel in double).  Answers match the oracle to 1e-9."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet, engine, planner
+
+    n = 60
+    names = [f"h{k:02d}" for k in range(n)]
+    bn = BayesNet(*[(names[k - 1], names[k]) for k in range(1, n)])
+    rng = np.random.default_rng(5)
+    bn.P[names[0]] = pd.Series({0: 0.3, 1: 0.3, 2: 0.4})
+    for k in range(1, n):
+        t = rng.dirichlet(np.ones(3) * 0.3, size=3)
+        bn.P[names[k]] = pd.DataFrame([(a, b, t[a, b]) for a in range(3) for b in range(3)], columns=[names[k - 1], names[k], "p"])
+    bn.prepare()
+    ev_vars = names[1:]
+    B = 40
+    rows = pd.DataFrame(rng.integers(0, 3, size=(B, n - 1)), columns=ev_vars)
+    got = bn.query_many(names[0], events=rows).to_numpy()
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    lik = bn.predict_proba(rows).to_numpy()
+    assert (lik < 1e-25).all() and (lik > 0).all()
+    for b in range(0, B, 3):
+        ev = {v: int(rows[v].iloc[b]) for v in ev_vars}
+        want = ve_oracle.query(dn, names[0], event=ev)[1].reshape(-1)
+        assert rel_err(got[b], want) < 1e-9
+        assert abs(lik[b] - ve_oracle.evidence_probability(dn, ev)) <= 1e-9 * lik[b]
+    # the float32 program does flag these rows (that is what routed them to float64)
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[names[0]]], [net.index[v] for v in ev_vars])
+    codes = np.stack([rows[v].to_numpy().astype(np.uint8) for v in ev_vars])
+    assert np.isnan(engine.Program(plan).run(codes, B)).all()
+    assert np.isfinite(engine.Program(plan, f64=True).run(codes, B)).all()
