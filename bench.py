@@ -180,6 +180,32 @@ def cpu_rate(workload: str, codes: np.ndarray, n_rows: int, n_procs: int):
     return n_rows / dt
 
 
+def effective_cores() -> int:
+    """Host cores this process may actually use: the smallest of the CPU count, the scheduler
+    affinity mask and the cgroup CPU quota (containers often expose 128 CPUs with a quota of 8)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]))))
+            else:
+                quota = int(parts[0])
+                if quota > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                        n = min(n, max(1, quota // int(g.read().split()[0])))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -211,7 +237,7 @@ def run_reference(args, rank, world):
 
     wl = workloads.WORKLOADS[args.workload]()
     bn = wl.build()
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     sample = args.cpu_rows or {"grid10x10": 512 * cores, "asia_1m": 20000 * cores, "dag50": 256 * cores}.get(args.workload, 256 * cores)
     codes = wl.codes(bn, sample, seed=0)
     for _ in range(max(0, min(args.warmup, 1))):
