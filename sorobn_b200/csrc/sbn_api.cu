@@ -300,6 +300,8 @@ bool plan_slab(sbn_program *P, StepDesc &st, int T, std::vector<int32_t> *words)
         else { sh.push_back(j); n_sh *= st.cards[j]; }
     }
     if (n_pa == 1 || n_pb == 1) return false;  // nothing is re-read: the plain tile walk is optimal
+    // small operands are re-read from L2 anyway (measured: B125 x B125 is faster without the slab)
+    if (static_cast<int64_t>(c0) * n_pa * st.cx < 512 || static_cast<int64_t>(c1) * n_pb * st.cx < 512) return false;
     const int64_t ma = static_cast<int64_t>(c0) * n_pa;
     const int64_t n_slab = ma * st.cx;
     if (n_slab * kSlabThreads * kRowsPerThread * 4 > kSlabSmemMax) return false;
