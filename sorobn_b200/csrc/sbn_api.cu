@@ -121,7 +121,7 @@ struct sbn_program {
     bool use_graph = true;
     bool use_tiled = true;
     bool use_slab = true;
-    int tiled_v = 2;  // 2 = preload schedule where available (default), 4 = always the x-loop schedule
+    bool use_preload = true;  // tiled kernel: operand preload schedule where instantiated (else the x-loop)
     cudaGraphExec_t exec = nullptr;
     struct {
         const uint8_t *ev;
@@ -556,8 +556,6 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
             d.ev_card[k] = in.ev[k].card;
         }
         for (size_t j = 0; j < in.strides.size(); ++j) d.stride[j] = in.strides[j];
-        d.cls = ((!in.strides.empty() && in.strides[0] != 0) ? 1 : 0) |
-                ((in.strides.size() > 1 && in.strides[1] != 0) ? 2 : 0);
         d.smem_off = -1;
         d.stage_floats = 0;
         if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
@@ -582,7 +580,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         q->n_bblocks = static_cast<int32_t>(n_rblocks);
         q->tile1 = 0;
         q->n_tile1 = 0;
-        if (st.slab && P->tiled_v == 2 && P->use_slab) {
+        if (st.slab && P->use_preload && P->use_slab) {
             // whole groups per CTA; 64-thread CTAs (128 rows) so that the slab fits shared memory
             const int64_t rows_slab = static_cast<int64_t>(kSlabThreads) * kRowsPerThread;
             const int64_t n_rb = (n_rows + rows_slab - 1) / rows_slab;
@@ -782,7 +780,7 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
         const int64_t chunks = (q.n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
         const int64_t grid = chunks * q.n_bblocks;
         if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
-        return launch_tiled(st, q, P->tiled_v == 2, grid, stream);
+        return launch_tiled(st, q, P->use_preload, grid, stream);
     }
     if (st.kind == 0) {
         const int threads = 256;
@@ -1290,7 +1288,7 @@ int sbn_program_set_tiled(sbn_program *P, int enabled) {
         P->exec = nullptr;
     }
     P->use_tiled = enabled != 0;
-    if (enabled == 4 || enabled == 2) P->tiled_v = enabled;
+    P->use_preload = enabled != 4;
     P->use_slab = enabled != 5;
     return SBN_OK;
 }

@@ -35,7 +35,7 @@ struct SbnInput {
     int32_t n_ev;                    // evidence axes gathered per row
     int32_t smem_off;                // float offset of the staged copy, -1 = read global
     int32_t stage_floats;            // floats copied by the bulk-TMA (multiple of 4)
-    int32_t cls;                     // tiled kernel: 0 = lacks axes 0 and 1, 1 = has axis 0, 2 = axis 1, 3 = both
+    int32_t pad_;
     int32_t ev_col[SBN_MAX_EV];
     int32_t ev_stride[SBN_MAX_EV];
     int32_t ev_card[SBN_MAX_EV];     // codes are clamped to card-1 (no out-of-bounds gather)
@@ -113,14 +113,16 @@ __device__ __forceinline__ float4 sbn_mul4(float4 a, float4 b) {
 }
 
 // ------------------------------------------------------------- batched step kernel
+// The general fallback (more than 4 inputs, two inputs spanning the tile, tables too
+// large for shared memory, tile table too large): no limits beyond SBN_MAX_IN / SBN_MAX_AXES.
 // Grid: 1-D, blockIdx.x = tile * n_bblocks + bblock (row blocks fastest so that
 // neighbouring CTAs stream neighbouring rows of the same scope entries).
 // One CTA = 512 evidence rows x one tile of outputs: all card[0] digits of axis 0,
-// `tile1` digits of axis 1, one combination of the remaining axes.  The planner puts
-// the axes that the largest batched input lacks first, so the tile re-reads that
-// input's entries and they stay in L1.
-// Thread = 4 consecutive rows (one float4) looping over the tile; the eliminated axis
-// is reduced in-thread (strided float4 loads, each fully coalesced across the warp).
+// `tile1` digits of axis 1, one combination of the remaining axes; the mixed-radix
+// decomposition of the tile index happens in registers (CTA-uniform).
+// Thread = 4 consecutive rows (one float4) looping over the tile, one output per
+// iteration; the eliminated axis is reduced in-thread (strided float4 loads, each fully
+// coalesced across the warp); operands shared by consecutive outputs are L1 hits.
 template <int N_IN, int CX>
 __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_constant__ SbnStep p) {
     extern __shared__ __align__(16) float s_tab[];
