@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 5
+#define SBN_ABI_VERSION 6
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -141,6 +141,17 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
 int sbn_gibbs_run_host(sbn_sampler *sampler, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
                        uint64_t seed, float *out, int64_t ld_out);
 void sbn_gibbs_destroy(sbn_sampler *sampler);
+
+/* The other sampling algorithms of `BayesNet.query` on the same sampler object:
+ * algo 0 = Gibbs (as above), 1 = likelihood weighting (bayes_net.py:621-663), 2 = rejection
+ * sampling (bayes_net.py:577-619); both built on forward sampling (bayes_net.py:518-548),
+ * n_iterations samples per evidence row.  A row of rejection sampling that keeps no sample
+ * is NaN (the reference returns an empty Series). */
+#define SBN_ALGO_GIBBS 0
+#define SBN_ALGO_LIKELIHOOD 1
+#define SBN_ALGO_REJECTION 2
+int sbn_sampler_run_host(sbn_sampler *sampler, int algo, const uint8_t *ev, int64_t ld_ev, int64_t n_rows,
+                         int64_t n_iterations, uint64_t seed, float *out, int64_t ld_out);
 
 /* Pinned host memory for evidence / posterior staging buffers. */
 int sbn_host_alloc(void **ptr, int64_t bytes);

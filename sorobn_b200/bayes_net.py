@@ -16,9 +16,10 @@ DataFrame); it is what the multi-GPU sharding and the benchmark drive.
 on the same kernels: the probability of a row is the normaliser of an elimination with the
 row as evidence.
 
-`algorithm="gibbs"` (bayes_net.py:665-737) runs one chain per evidence row on the device
-(csrc/sbn_gibbs.cuh).  Likelihood weighting / rejection sampling (:577-663) and
-`fit` / `partial_fit` / `sample` are outside this round's scope (scope table).
+The approximate algorithms run on the device too (csrc/sbn_gibbs.cuh): `algorithm="gibbs"`
+(bayes_net.py:665-737) one chain per evidence row, `"likelihood"` (:621-663) and `"rejection"`
+(:577-619) n_iterations forward samples per row.  `fit` / `partial_fit` / `sample` are outside
+this round's scope (scope table).
 """
 from __future__ import annotations
 
@@ -279,16 +280,15 @@ class BayesNet:
         for q in query:
             if q in event:
                 raise ValueError("A query variable cannot be part of the event")
-        if algorithm == "gibbs":
-            freq = self._gibbs(query, tuple(event), [[event[v]] for v in event], 1, n_iterations)
-            answer = pd.Series(freq[0][:, 0].astype(np.float64), index=freq[1],
-                               name=f"P({', '.join(map(str, query))})")
-            return answer[answer > 0]  # the reference only lists the states the chain visited
+        if algorithm in ("gibbs", "likelihood", "rejection"):
+            freq = self._sample_query(algorithm, query, tuple(event), [[event[v]] for v in event], 1, n_iterations)
+            values = freq[0][:, 0].astype(np.float64)
+            name = f"P({', '.join(map(str, query))})"
+            if np.isnan(values).any():  # rejection sampling kept no sample: the reference's answer is empty
+                return pd.Series([], index=freq[1][:0], name=name, dtype=np.float64)
+            answer = pd.Series(values, index=freq[1], name=name)
+            return answer[answer > 0]  # the reference only lists the states that were sampled
         if algorithm != "exact":
-            if algorithm in ("likelihood", "rejection"):
-                raise NotImplementedError(
-                    f"algorithm={algorithm!r} is outside the CUDA path (exact and gibbs are implemented; DESIGN.md)"
-                )
             raise ValueError("Unknown algorithm, must be one of: exact, gibbs, likelihood, rejection")
 
         ev_vars = tuple(event)
@@ -304,9 +304,10 @@ class BayesNet:
             return answer.iloc[:0]
         return answer[post > 0]
 
-    def _gibbs(self, query, ev_vars, columns, n_rows, n_iterations):
-        """One Gibbs chain per evidence row on the device (bayes_net.py:665-737): returns
-        (frequencies [Q, n_rows], answer index)."""
+    def _sample_query(self, algorithm, query, ev_vars, columns, n_rows, n_iterations):
+        """The approximate algorithms on the device, per evidence row: one Gibbs chain
+        (bayes_net.py:665-737), or n_iterations forward samples for likelihood weighting
+        (:621-663) / rejection sampling (:577-619).  Returns (estimates [Q, n_rows], index)."""
         if self._compiled is None:
             self._compile()
             if self._compiled is None:
@@ -315,22 +316,20 @@ class BayesNet:
         for name in (*query, *ev_vars):
             if name not in net.index:
                 raise KeyError(name)
-        key = ("gibbs", tuple(query), tuple(ev_vars))
+        key = ("sampler", tuple(query), tuple(ev_vars))
         sampler = self._engine_cache.get(key)
         q_sorted = sorted(query, key=str)
         if sampler is None:
             from . import engine
 
-            nonevents = sorted(set(self.nodes) - set(ev_vars))  # bayes_net.py:697, the cycle order
-            if not nonevents:
-                raise ValueError("every variable is observed: nothing to sample")
+            nonevents = sorted(set(self.nodes) - set(ev_vars))  # bayes_net.py:697, the Gibbs cycle order
             sampler = engine.GibbsSampler(net, [net.index[q] for q in q_sorted], [net.index[e] for e in ev_vars],
                                           [net.index[v] for v in nonevents], device=self.device)
             self._engine_cache[key] = sampler
         codes, bad = self._encode_events(ev_vars, columns)
         if bad.any():
             raise ValueError("an event value is not a state of its variable")
-        freq = sampler.run(codes, n_rows, n_iterations, self._rng.getrandbits(63))
+        freq = sampler.run(codes, n_rows, n_iterations, self._rng.getrandbits(63), algorithm=algorithm)
         doms = [net.domains[net.index[q]] for q in q_sorted]
         index = pd.Index(doms[0], name=q_sorted[0]) if len(q_sorted) == 1 else pd.MultiIndex.from_product(doms, names=q_sorted)
         return freq, index
@@ -346,12 +345,12 @@ class BayesNet:
         for q in query:
             if q in ev_vars:
                 raise ValueError("A query variable cannot be part of the event")
-        if algorithm == "gibbs":
-            freq, index = self._gibbs(query, ev_vars, [events[v].to_numpy() for v in ev_vars], len(events.index),
-                                      n_iterations)
+        if algorithm in ("gibbs", "likelihood", "rejection"):
+            freq, index = self._sample_query(algorithm, query, ev_vars, [events[v].to_numpy() for v in ev_vars],
+                                             len(events.index), n_iterations)
             return pd.DataFrame(freq.T.astype(np.float64), index=events.index, columns=index)
         if algorithm != "exact":
-            raise NotImplementedError("query_many implements algorithm='exact' and 'gibbs'")
+            raise ValueError("Unknown algorithm, must be one of: exact, gibbs, likelihood, rejection")
         plan, program = self._plan(query, ev_vars, _planner.MODE_BATCHED)
         n = len(events.index)
         if n == 0:

@@ -1423,6 +1423,7 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
     S->query = S->d_ints + o_q;
     S->ev_var = S->d_ints + o_ev;
     SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBN_CUDA_S(cudaFuncSetAttribute(sbn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #undef SBN_CUDA_S
     *out = S;
     return SBN_OK;
@@ -1439,9 +1440,10 @@ void sbn_gibbs_destroy(sbn_sampler *S) {
     delete S;
 }
 
-int sbn_gibbs_run_host(sbn_sampler *S, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
+static int sampler_run(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
                        uint64_t seed, float *out, int64_t ld_out) {
     if (!S || !out) return fail(SBN_E_INVALID, "null argument");
+    if (algo < 0 || algo > 2) return fail(SBN_E_INVALID, "unknown sampling algorithm %d", algo);
     if (n_chains <= 0 || n_iterations <= 0) return fail(SBN_E_INVALID, "n_chains and n_iterations must be positive");
     if (S->n_ev > 0 && (!ev || (S->n_ev > 1 && ld_ev < n_chains))) return fail(SBN_E_INVALID, "bad evidence");
     if (S->Q > 1 && ld_out < n_chains) return fail(SBN_E_INVALID, "ld_out < n_chains");
@@ -1484,15 +1486,32 @@ int sbn_gibbs_run_host(sbn_sampler *S, const uint8_t *ev, int64_t ld_ev, int64_t
     g.n_chains = n_chains;
     g.n_iterations = n_iterations;
     g.seed = seed;
-    const size_t smem = ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(S->Q) * SBN_GIBBS_THREADS * 4;
-    const int64_t grid = (n_chains + SBN_GIBBS_THREADS - 1) / SBN_GIBBS_THREADS;
-    sbn_gibbs_kernel<<<static_cast<unsigned>(grid), SBN_GIBBS_THREADS, smem, S->stream>>>(g);
+    if (algo == 0) {
+        const size_t smem = ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(S->Q) * SBN_GIBBS_THREADS * 4;
+        const int64_t grid = (n_chains + SBN_GIBBS_THREADS - 1) / SBN_GIBBS_THREADS;
+        sbn_gibbs_kernel<<<static_cast<unsigned>(grid), SBN_GIBBS_THREADS, smem, S->stream>>>(g);
+    } else {
+        // one CTA per evidence row; its threads share the row's n_iterations samples
+        const size_t smem = ((static_cast<size_t>(S->n_vars) * (SBN_GIBBS_THREADS + 1) + 15) / 16) * 16 + static_cast<size_t>(S->Q) * 8;
+        if (smem > 200 * 1024) return fail(SBN_E_INVALID, "sampler state needs %zu bytes of shared memory", smem);
+        sbn_forward_kernel<<<static_cast<unsigned>(n_chains), SBN_GIBBS_THREADS, smem, S->stream>>>(g, algo);
+    }
     SBN_CUDA(cudaGetLastError());
     S->launches++;
     SBN_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(ld_out) * 4, S->d_out, static_cast<size_t>(n_chains) * 4,
                                static_cast<size_t>(n_chains) * 4, static_cast<size_t>(S->Q), cudaMemcpyDeviceToHost, S->stream));
     SBN_CUDA(cudaStreamSynchronize(S->stream));
     return SBN_OK;
+}
+
+int sbn_gibbs_run_host(sbn_sampler *S, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
+                       uint64_t seed, float *out, int64_t ld_out) {
+    return sampler_run(S, 0, ev, ld_ev, n_chains, n_iterations, seed, out, ld_out);
+}
+
+int sbn_sampler_run_host(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_ev, int64_t n_rows, int64_t n_iterations,
+                         uint64_t seed, float *out, int64_t ld_out) {
+    return sampler_run(S, algo, ev, ld_ev, n_rows, n_iterations, seed, out, ld_out);
 }
 
 }  // extern "C"

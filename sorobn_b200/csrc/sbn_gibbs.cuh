@@ -170,3 +170,93 @@ __global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_gibbs_kernel(const __gr
     const float inv = 1.0f / static_cast<float>(p.n_iterations);
     for (int q = 0; q < p.Q; ++q) p.out[static_cast<int64_t>(q) * p.ld_out + chain] = static_cast<float>(counts[q * T]) * inv;
 }
+
+
+// ------------------------------------------------- forward-sampling based estimators
+// `BayesNet._forward_sample` (bayes_net.py:518-548) draws the variables in topological
+// order; a variable named in `init` takes that value instead of being drawn, and the sample's
+// "likelihood" is the product of P(value | parents) over ALL variables, i.e. the joint
+// probability of the sample.
+//   algo 1, likelihood weighting (bayes_net.py:621-663): samples with init = event; the
+//           answer is, per joint query state, the MEAN likelihood of the samples that landed
+//           there, normalised over the states (the reference's estimator, kept as is);
+//   algo 2, rejection sampling (bayes_net.py:577-619): unconstrained samples; those that
+//           contradict the event are dropped; the answer is the frequency of each query state
+//           among the kept ones (NaN when none is kept: the reference returns an empty Series).
+// One CTA per evidence row, its threads share the row's samples; per-state sums live in
+// shared memory (atomics, low contention).
+__global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_forward_kernel(const __grid_constant__ SbnGibbs p, int algo) {
+    extern __shared__ uint8_t s_raw[];
+    const int T = SBN_GIBBS_THREADS;
+    uint8_t *state = s_raw + threadIdx.x;                                             // [n_vars][T]
+    uint8_t *evcode = s_raw + static_cast<size_t>(p.n_vars) * T;                      // [n_vars], 0xff = free
+    float *acc_sum = reinterpret_cast<float *>(s_raw + ((static_cast<size_t>(p.n_vars) * (T + 1) + 15) / 16) * 16);  // [Q]
+    uint32_t *acc_cnt = reinterpret_cast<uint32_t *>(acc_sum + p.Q);                  // [Q]
+    const int64_t row = blockIdx.x;
+
+    for (int v = threadIdx.x; v < p.n_vars; v += T) evcode[v] = 0xff;
+    for (int q = threadIdx.x; q < p.Q; q += T) {
+        acc_sum[q] = 0.f;
+        acc_cnt[q] = 0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.n_ev; k += T) {
+        const int v = p.ev_var[k];
+        evcode[v] = static_cast<uint8_t>(min(static_cast<int>(p.ev[static_cast<int64_t>(k) * p.ld_ev + row]), p.card[v] - 1));
+    }
+    __syncthreads();
+
+    for (int64_t it = threadIdx.x; it < p.n_iterations; it += T) {
+        SbnRng rng;
+        rng.init(p.seed, static_cast<uint64_t>(row) * static_cast<uint64_t>(p.n_iterations) + static_cast<uint64_t>(it));
+        float lik = 1.f;
+        bool keep = true;
+        for (int v = 0; v < p.n_vars; ++v) {
+            int base = p.cpt_off[v];
+            for (int k = p.par_ptr[v]; k < p.par_ptr[v + 1]; ++k) base += state[p.par_idx[k] * T] * p.par_stride[k];
+            const int c = p.card[v];
+            int x;
+            if (algo == 1 && evcode[v] != 0xff) {
+                x = evcode[v];
+            } else {
+                const float u = rng.uniform();
+                float acc = 0.f;
+                x = c - 1;
+                for (int j = 0; j < c; ++j) {
+                    acc += __ldg(p.tables + base + j);
+                    if (u <= acc) {
+                        x = j;
+                        break;
+                    }
+                }
+                if (algo == 2 && evcode[v] != 0xff && x != evcode[v]) keep = false;
+            }
+            lik *= __ldg(p.tables + base + x);
+            state[v * T] = static_cast<uint8_t>(x);
+        }
+        int qi = 0;
+        for (int k = 0; k < p.n_query; ++k) qi = qi * p.card[p.query[k]] + state[p.query[k] * T];
+        if (algo == 1) {
+            atomicAdd(&acc_sum[qi], lik);
+            atomicAdd(&acc_cnt[qi], 1u);
+        } else if (keep) {
+            atomicAdd(&acc_cnt[qi], 1u);
+        }
+    }
+    __syncthreads();
+    // normalise: likelihood -> per-state mean, then over the states; rejection -> frequency
+    __shared__ float s_total;
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int q = 0; q < p.Q; ++q) {
+            const float v = algo == 1 ? (acc_cnt[q] ? acc_sum[q] / static_cast<float>(acc_cnt[q]) : 0.f)
+                                      : static_cast<float>(acc_cnt[q]);
+            acc_sum[q] = v;
+            total += v;
+        }
+        s_total = total;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < p.Q; q += T)
+        p.out[static_cast<int64_t>(q) * p.ld_out + row] = s_total > 0.f ? acc_sum[q] / s_total : __int_as_float(0x7fc00000);
+}

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class EngineError(RuntimeError):
@@ -77,6 +77,8 @@ def load():
     lib.sbn_gibbs_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, i32, vp, c.POINTER(vp)]
     lib.sbn_gibbs_run_host.restype = i32
     lib.sbn_gibbs_run_host.argtypes = [vp, vp, i64, i64, i64, c.c_uint64, vp, i64]
+    lib.sbn_sampler_run_host.restype = i32
+    lib.sbn_sampler_run_host.argtypes = [vp, i32, vp, i64, i64, i64, c.c_uint64, vp, i64]
     lib.sbn_gibbs_destroy.restype = None
     lib.sbn_gibbs_destroy.argtypes = [vp]
     lib.sbn_host_alloc.restype = i32
@@ -94,7 +96,7 @@ EXPORTS = (
     "sbn_program_run_host_f64", "sbn_program_evidence_host", "sbn_program_evidence_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
     "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_gibbs_create", "sbn_gibbs_run_host",
-    "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
+    "sbn_sampler_run_host", "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
 )
 
 
@@ -263,7 +265,8 @@ class GibbsSampler:
         par_idx = np.ascontiguousarray(par_idx, dtype=np.int32)
         self.query = np.ascontiguousarray(query_ids, dtype=np.int32)
         self.evidence = np.ascontiguousarray(evidence_ids, dtype=np.int32)
-        cycle = np.ascontiguousarray(cycle_ids, dtype=np.int32)
+        # the cycle is only walked by Gibbs; keep the C side's "non-empty" contract when all is observed
+        cycle = np.ascontiguousarray(cycle_ids if len(cycle_ids) else query_ids, dtype=np.int32)
         self.Q = int(np.prod([net.card[q] for q in query_ids]))
         self.n_ev = len(evidence_ids)
         self._h = ctypes.c_void_p()
@@ -273,15 +276,18 @@ class GibbsSampler:
             self.n_ev, self.evidence.ctypes.data if self.n_ev else None, len(cycle), cycle.ctypes.data,
             ctypes.byref(self._h)))
 
-    def run(self, codes: np.ndarray, n_chains: int, n_iterations: int, seed: int) -> np.ndarray:
-        """uint8 codes [n_ev, n_chains] -> frequencies float32 [Q, n_chains]."""
+    ALGORITHMS = {"gibbs": 0, "likelihood": 1, "rejection": 2}
+
+    def run(self, codes: np.ndarray, n_chains: int, n_iterations: int, seed: int, algorithm: str = "gibbs") -> np.ndarray:
+        """uint8 codes [n_ev, n_rows] -> estimated posterior float32 [Q, n_rows] (one Gibbs
+        chain, or n_iterations forward samples, per evidence row)."""
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         if self.n_ev and codes.shape != (self.n_ev, n_chains):
             raise ValueError(f"evidence codes have shape {codes.shape}, expected {(self.n_ev, n_chains)}")
         out = np.empty((self.Q, n_chains), dtype=np.float32)
-        _check(load().sbn_gibbs_run_host(self._h, codes.ctypes.data if self.n_ev else None, n_chains, n_chains,
-                                         int(n_iterations), ctypes.c_uint64(int(seed) & (2**64 - 1)), out.ctypes.data,
-                                         n_chains))
+        _check(load().sbn_sampler_run_host(self._h, self.ALGORITHMS[algorithm], codes.ctypes.data if self.n_ev else None,
+                                           n_chains, n_chains, int(n_iterations),
+                                           ctypes.c_uint64(int(seed) & (2**64 - 1)), out.ctypes.data, n_chains))
         return out
 
     def close(self):

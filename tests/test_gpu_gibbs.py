@@ -72,3 +72,91 @@ def test_gibbs_on_the_benchmark_grid_runs_and_tracks_exact():
     assert np.allclose(gibbs.sum(axis=1), 1.0, atol=1e-5)
     # 70 non-event variables share the iterations: ~2000 draws of the query variable per chain
     assert np.abs(gibbs - exact).mean() < 0.03
+
+
+def _lw_reference_estimator(bn, query, event):
+    """Exact expectation of the reference's likelihood-weighting estimator
+    (bayes_net.py:621-663), by enumeration: samples are drawn from g(s) = prod over non-event
+    variables of P(v | parents) with the event clamped, each is weighted by the JOINT
+    probability P(s) (bayes_net.py:546 multiplies over all variables), the per-state MEAN
+    weight is taken (:660) and normalised (:661)."""
+    import itertools
+
+    net = bn._compiled
+    names = net.names
+    doms = [range(int(c)) for c in net.card]
+    qids = sorted((net.index[q] for q in query), key=lambda v: names[v])
+    ev = {net.index[k]: net.domains[net.index[k]].index(v) for k, v in event.items()}
+    num = {}
+    den = {}
+    for s in itertools.product(*doms):
+        if any(s[v] != x for v, x in ev.items()):
+            continue
+        joint, g = 1.0, 1.0
+        for v in range(len(names)):
+            p = net.cpt[v][tuple(s[u] for u in net.parents[v]) + (s[v],)]
+            joint *= p
+            if v not in ev:
+                g *= p
+        key = tuple(s[v] for v in qids)
+        num[key] = num.get(key, 0.0) + g * joint
+        den[key] = den.get(key, 0.0) + g
+    means = {k: num[k] / den[k] for k in num if den[k] > 0}
+    total = sum(means.values())
+    return {k: v / total for k, v in means.items()}
+
+
+def test_rejection_sampling_converges_to_exact_posterior():
+    from sorobn_b200 import examples
+
+    for make, query, event in ((examples.sprinkler, ("Rain",), {"Sprinkler": True}),
+                               (examples.grades, ("Grade",), {"Letter": "Strong", "SAT": "Success"}),
+                               (examples.asia, ("Bronchitis",), {"Smoker": True, "Dispnea": True})):
+        bn = make(seed=11)
+        exact = bn.query(*query, event=event)
+        got = bn.query(*query, event=event, algorithm="rejection", n_iterations=2_000_000)
+        both = pd.concat([exact, got], axis=1).fillna(0.0)
+        assert np.isclose(got.sum(), 1.0, atol=1e-5)
+        assert np.abs(both.iloc[:, 0] - both.iloc[:, 1]).max() < 0.01, both
+    # an event that never shows up: the reference's answer is empty
+    bn = examples.asia(seed=1)
+    assert len(bn.query("Smoker", event={"TB or cancer": False, "Lung cancer": True}, algorithm="rejection",
+                        n_iterations=10_000)) == 0
+
+
+def test_likelihood_weighting_matches_the_reference_estimator():
+    from sorobn_b200 import examples
+
+    for make, query, event in ((examples.sprinkler, ("Rain",), {"Sprinkler": True}),
+                               (examples.alarm, ("Burglary",), {"John calls": True, "Mary calls": True}),
+                               (examples.grades, ("Letter", "SAT"), {"Intelligence": "Smart"})):
+        bn = make(seed=5)
+        want = _lw_reference_estimator(bn, query, event)
+        got = bn.query(*query, event=event, algorithm="likelihood", n_iterations=2_000_000)
+        net = bn._compiled
+        assert np.isclose(got.sum(), 1.0, atol=1e-5)
+        for key, p in want.items():
+            names = sorted(query)
+            label = tuple(net.domains[net.index[n]][k] for n, k in zip(names, key))
+            value = got[label if len(label) > 1 else label[0]]
+            assert abs(value - p) < 0.01, (query, label, value, p)
+
+
+def test_every_algorithm_answers_like_the_reference_check_query():
+    # reference check_query (test_bayes_net.py:66-76): every algorithm returns an answer
+    from sorobn_b200 import examples
+
+    for make in (examples.alarm, examples.asia, examples.sprinkler, examples.grades):
+        bn = make(seed=3)
+        fjd = bn.full_joint_dist()
+        event = dict(zip(fjd.index.names, fjd.index[0]))
+        query = sorted(event)[0]
+        del event[query]
+        for algorithm in ("exact", "gibbs", "likelihood", "rejection"):
+            ans = bn.query(query, event=event, algorithm=algorithm, n_iterations=2000)
+            assert ans.name == f"P({query})"
+            if len(ans):
+                assert np.isclose(ans.sum(), 1.0, atol=1e-5)
+    many = examples.alarm(seed=2).query_many("Alarm", events=pd.DataFrame({"John calls": [True, False, True]}),
+                                             algorithm="likelihood", n_iterations=20_000)
+    assert many.shape == (3, 2) and np.allclose(many.sum(axis=1), 1.0, atol=1e-5)
