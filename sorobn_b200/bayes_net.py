@@ -18,8 +18,8 @@ row as evidence.
 
 The approximate algorithms run on the device too (csrc/sbn_gibbs.cuh): `algorithm="gibbs"`
 (bayes_net.py:665-737) one chain per evidence row, `"likelihood"` (:621-663) and `"rejection"`
-(:577-619) n_iterations forward samples per row.  `fit` / `partial_fit` / `sample` are outside
-this round's scope (scope table).
+(:577-619) n_iterations forward samples per row.  `fit` / `partial_fit` / `sample`
+(:467-575) stay on the host (pandas / numpy), as in the reference.
 """
 from __future__ import annotations
 
@@ -215,6 +215,72 @@ class BayesNet:
             cpt=cpts,
         )
         self._engine_cache = OrderedDict()
+
+    # ------------------------------------------------------------- learning / sampling
+    def partial_fit(self, X: pd.DataFrame) -> "BayesNet":
+        """Update every CPT from a batch of rows (host side, pandas; bayes_net.py:467-510).
+
+        Counts are kept per node (`_P_sizes` holds the number of rows behind every parent
+        configuration), so feeding the data in chunks gives the same tables as one `fit`.
+        With `prior_count`, every combination of the values seen in the first batch gets one
+        pseudo-observation, as in the reference."""
+        for child, parents in self.parents.items():
+            scope = [*parents, child]
+            seen = X.groupby(scope).size()
+            if child in self.P:
+                counts = (self.P[child] * self._P_sizes[child]).add(seen, fill_value=0)
+            else:
+                counts = seen
+                if self.prior_count:
+                    grid = pd.MultiIndex.from_product([X[v].unique() for v in scope], names=scope)
+                    counts = counts.add(pd.Series(1, index=grid), fill_value=0)
+            totals = counts.groupby(parents).sum()
+            self._P_sizes[child] = totals
+            self.P[child] = counts / totals
+        for root in self.roots:
+            if root in self.P:
+                counts = (self.P[root] * self._P_sizes[root]).add(X[root].value_counts(), fill_value=0)
+                self._P_sizes[root] += len(X)
+                self.P[root] = counts / self._P_sizes[root]
+            else:
+                self._P_sizes[root] = len(X)
+                self.P[root] = X[root].value_counts(normalize=True)
+        self.prepare()
+        return self
+
+    def fit(self, X: pd.DataFrame) -> "BayesNet":
+        """Estimate every CPT from `X` (bayes_net.py:512-516)."""
+        self.P = {}
+        self._P_sizes = {}
+        return self.partial_fit(X)
+
+    def sample(self, n=1, init: dict | None = None, method="forward"):
+        """Forward (ancestral) samples (bayes_net.py:550-575): a Series for n == 1, otherwise a
+        DataFrame with the columns sorted.  Variables named in `init` keep the given value.
+        Vectorised over the n samples on the host; the stream comes from `seed`."""
+        if method != "forward":
+            raise ValueError("Unknown method, must be one of: forward")
+        if self._compiled is None:
+            self._compile()
+            if self._compiled is None:
+                raise ValueError("every node needs a CPT in P before sampling; call prepare()")
+        net = self._compiled
+        init = init or {}
+        rng = np.random.default_rng(self._rng.getrandbits(63))
+        n = int(n)
+        codes = np.zeros((len(net.names), n), dtype=np.int64)
+        for v, name in enumerate(net.names):
+            if name in init:
+                codes[v] = net.domains[v].index(init[name])
+                continue
+            table = net.cpt[v]
+            probs = table[tuple(codes[p] for p in net.parents[v])] if net.parents[v] else np.broadcast_to(table, (n, table.shape[-1]))
+            cdf = np.cumsum(probs, axis=-1)
+            u = rng.random((n, 1)) * cdf[:, -1:]
+            codes[v] = np.minimum((u > cdf).sum(axis=-1), table.shape[-1] - 1)
+        frame = pd.DataFrame({name: np.asarray(net.domains[v], dtype=object)[codes[v]] for v, name in enumerate(net.names)})
+        frame = frame.infer_objects().sort_index(axis="columns")
+        return frame if n > 1 else frame.iloc[0]
 
     # ---------------------------------------------------------------------- query
     def _plan(self, query, evidence_vars, mode, robust=False):

@@ -207,3 +207,45 @@ def test_program_validation_rejects_malformed_programs():
     # a well-formed program fails only because there is no device here (or succeeds on a GPU box)
     rc, msg = create(plan.words)
     assert rc in (0, -4), msg
+
+
+@pytest.mark.parametrize("make", ALL, ids=lambda f: f.__name__)
+def test_fit_partial_fit_and_sample(make):
+    # reference check_partial_fit / check_sample_many / check_sample_one (test_bayes_net.py:15-44)
+    import copy
+
+    bn = make()
+    bn.seed = 1
+    one = bn.sample()
+    assert isinstance(one, pd.Series) and sorted(one.index) == sorted(bn.nodes)
+    for n in (2, 3, 100):
+        frame = bn.sample(n)
+        assert len(frame) == n and sorted(frame.columns) == sorted(bn.nodes)
+    clamp = {bn.nodes[-1]: bn._compiled.domains[len(bn.nodes) - 1][0]}
+    assert (bn.sample(50, init=clamp)[bn.nodes[-1]] == clamp[bn.nodes[-1]]).all()
+
+    incremental = copy.deepcopy(bn)
+    samples = bn.sample(500)
+    bn.fit(samples)
+    incremental.P = {}
+    for rows in np.array_split(np.arange(len(samples)), 5):
+        incremental.partial_fit(samples.iloc[rows])
+    for node in bn.P:
+        pd.testing.assert_series_equal(bn.P[node], incremental.P[node])
+    # the fitted tables are proper CPTs and compile for the device
+    for child, parents in bn.parents.items():
+        assert np.allclose(bn.P[child].groupby(parents).sum(), 1)
+    assert bn._compiled is not None
+
+
+def test_fit_recovers_the_generating_tables_and_prior_count():
+    from sorobn_b200 import examples
+
+    truth = examples.sprinkler(seed=4)
+    data = truth.sample(20_000)
+    learned = BayesNet(*[(p, c) for c, ps in truth.parents.items() for p in ps]).fit(data)
+    for node in truth.P:
+        a, b = truth.P[node], learned.P[node].reindex(truth.P[node].index).fillna(0)
+        assert np.abs(a - b).max() < 0.03, node
+    smooth = BayesNet(*[(p, c) for c, ps in truth.parents.items() for p in ps], prior_count=1).fit(data.iloc[:50])
+    assert (smooth.P["Wet grass"] > 0).all()  # every combination got a pseudo-observation
