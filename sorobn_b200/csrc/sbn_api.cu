@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -570,7 +571,11 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
         // enough CTAs for ~4 waves (148 SMs x ~6 resident CTAs), otherwise as many
         // consecutive tiles per CTA as possible (neighbouring tiles share operands in L1)
-        const int64_t target = 4 * 148 * 6;
+        static const int64_t target_env = [] {
+            const char *e = getenv("SOROBN_B200_TARGET_CTAS");
+            return e ? atoll(e) : 0LL;
+        }();
+        const int64_t target = target_env > 0 ? target_env : 4 * 148 * 6;
         int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(st.n_tiles, target / std::max<int64_t>(1, n_rblocks)));
         int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
         q->tiles_per_cta = static_cast<int32_t>(tpc);
