@@ -273,6 +273,17 @@ constexpr int kTiledMaxIn = 4;
 constexpr int kRowsPerThread = 2;
 constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 
+// CTA size of the regular tiled launches (the kernel reads blockDim.x); 128 unless overridden
+// for experiments
+int tiled_threads() {
+    static const int v = [] {
+        const char *e = getenv("SOROBN_B200_TILED_THREADS");
+        const int t = e ? atoi(e) : 0;
+        return (t == 32 || t == 64 || t == 128) ? t : SBN_TILED_THREADS;
+    }();
+    return v;
+}
+
 constexpr int kSlabThreads = 64;                 // CTA size of the slab variant (x kRowsPerThread rows)
 constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one slab may take
 
@@ -567,7 +578,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     }
     q->smem_floats = smem;
     if (tiled) {
-        const int64_t rows_per_cta = static_cast<int64_t>(SBN_TILED_THREADS) * kRowsPerThread;
+        const int64_t rows_per_cta = static_cast<int64_t>(tiled_threads()) * kRowsPerThread;
         const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
         // enough CTAs for ~8 waves (148 SMs x ~6 resident CTAs), otherwise as many
         // consecutive tiles per CTA as possible (neighbouring tiles share operands in L1)
@@ -682,7 +693,7 @@ constexpr int kV = kRowsPerThread;  // evidence rows per thread of the tiled ker
 template <int NU, int NA, int NB, int NC>
 cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t grid, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
-    const dim3 g(static_cast<unsigned>(grid)), b(SBN_TILED_THREADS);
+    const dim3 g(static_cast<unsigned>(grid)), b(tiled_threads());
     if constexpr (NC > 0) {
         switch (tile) {
             case 2: sbn_step_tiled<NU, NA, NB, NC, 2, kV, 0><<<g, b, smem, stream>>>(q); break;

@@ -252,3 +252,57 @@ def test_programs_without_query_variables_give_the_evidence_probability():
             assert want == 0 or post[0, b] == 1.0
     with pytest.raises(ValueError):
         planner.build_plan(net, [], [], allow_empty_query=True)
+
+
+def test_planner_limits_raise_clear_errors():
+    import pandas as pd
+
+    # a variable with more than 255 states cannot be evidence (state codes are uint8)
+    big = BayesNet(("A", "B"))
+    big.P["A"] = pd.Series({k: 1 / 300 for k in range(300)})
+    big.P["B"] = pd.DataFrame([(a, b, 0.5) for a in range(300) for b in (0, 1)], columns=["A", "B", "p"])
+    big.prepare()
+    net = big._compiled
+    with pytest.raises(ValueError, match="uint8"):
+        planner.build_plan(net, [net.index["B"]], [net.index["A"]])
+    assert planner.build_plan(net, [net.index["A"]], [net.index["B"]]).Q == 300  # querying it is fine
+    # duplicate and overlapping variables
+    net = examples.alarm()._compiled
+    a, b = net.index["Alarm"], net.index["Burglary"]
+    with pytest.raises(ValueError):
+        planner.build_plan(net, [a, a], [])
+    with pytest.raises(ValueError):
+        planner.build_plan(net, [a], [b, b])
+    with pytest.raises(ValueError):
+        planner.build_plan(net, [a], [a])
+    # a factor wider than the kernel's axis limit
+    wide = BayesNet(*[(f"p{k:02d}", "child") for k in range(planner.MAX_AXES + 1)])
+    for k in range(planner.MAX_AXES + 1):
+        wide.P[f"p{k:02d}"] = pd.Series({0: 0.5, 1: 0.5})
+    wide.parents  # the CPT of `child` would have 2**22 rows: build the plan from a stub net instead
+    stub = planner.CompiledNet(
+        names=[f"p{k:02d}" for k in range(planner.MAX_AXES + 1)] + ["child"],
+        domains=[[0, 1]] * (planner.MAX_AXES + 2),
+        parents=[[] for _ in range(planner.MAX_AXES + 1)] + [list(range(planner.MAX_AXES + 1))],
+        cpt=[np.array([0.5, 0.5])] * (planner.MAX_AXES + 1) + [np.zeros((1,))],
+    )
+    with pytest.raises(ValueError, match="axes"):
+        planner.build_plan(stub, list(range(planner.MAX_AXES + 1)), [], mode=planner.MODE_FLAT)
+
+
+def test_every_step_respects_the_kernel_limits():
+    for name in ("grid10x10", "asia_1m", "dag50"):
+        wl = workloads.WORKLOADS[name]()
+        bn = wl.build()
+        net = bn._compiled
+        for mode in (planner.MODE_BATCHED, planner.MODE_FLAT):
+            plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence], mode=mode)
+            for st in plan.steps:
+                assert 1 <= len(st.inputs) <= planner.MAX_IN
+                assert len(st.cards) <= planner.MAX_AXES
+                assert all(len(f.ev) <= planner.MAX_EV for f, _, _ in st.inputs)
+                if mode == planner.MODE_FLAT:
+                    assert st.kind == planner.KIND_FLAT
+            # slot sizes cover what is written into them
+            for st in plan.steps:
+                assert plan.slots[st.out_slot][1] >= (int(np.prod(st.cards, dtype=np.int64)) if st.cards else 1)
