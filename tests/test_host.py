@@ -249,3 +249,28 @@ def test_fit_recovers_the_generating_tables_and_prior_count():
         assert np.abs(a - b).max() < 0.03, node
     smooth = BayesNet(*[(p, c) for c, ps in truth.parents.items() for p in ps], prior_count=1).fit(data.iloc[:50])
     assert (smooth.P["Wet grass"] > 0).all()  # every combination got a pseudo-observation
+
+
+def test_chow_liu_matches_reference_edges():
+    """structure.chow_liu against the edges the REAL reference returned on the same seeded
+    samples (tests/golden/chow_liu.json), plus the defining properties of the tree."""
+    import json
+
+    from sorobn_b200 import structure
+
+    with open(os.path.join(ROOT, "tests", "golden", "chow_liu.json")) as f:
+        golden = json.load(f)
+    for case in golden["cases"]:
+        bn = getattr(examples, case["network"])(seed=case["seed"])
+        X = bn.sample(case["n"])
+        edges = structure.chow_liu(X, root=case["root"])
+        assert sorted(map(tuple, edges)) == sorted(map(tuple, case["edges"])), case["network"]
+        # a spanning tree oriented away from the root: n - 1 edges, every node but the root has one parent
+        assert len(edges) == len(X.columns) - 1
+        children = [c for _, c in edges]
+        root = case["root"] if case["root"] is not None else X.columns[0]
+        assert sorted(children + [root]) == sorted(X.columns)
+    # learning a network from the tree and querying it stays on the normal path
+    X = examples.sprinkler(seed=9).sample(4000)
+    learned = BayesNet(*structure.chow_liu(X)).fit(X)
+    assert learned.is_tree and learned._compiled is not None
