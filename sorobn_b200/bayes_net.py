@@ -118,6 +118,22 @@ class BayesNet:
         blanket.discard(node)
         return sorted(blanket)
 
+    def graphviz(self):
+        """The structure as a `graphviz.Digraph` (bayes_net.py:910-929); the module is imported
+        here, so it is only needed when this is called."""
+        import graphviz
+
+        g = graphviz.Digraph()
+        for node in self.nodes:
+            g.node(str(node))
+        for parent, kids in self.children.items():
+            for kid in kids:
+                g.edge(str(parent), str(kid))
+        return g
+
+    def _repr_svg_(self):
+        return self.graphviz()
+
     def iter_dfs(self):
         """Depth-first walk from each root (bayes_net.py:1041-1075)."""
         seen = set()
