@@ -629,13 +629,40 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     }
 }
 
+// Launch with the programmatic-dependent-launch attribute when enabled: the kernel may then be
+// scheduled while its predecessor on the stream is still draining; it calls
+// griddepcontrol.wait before touching anything a predecessor wrote (see sbn_pdl_wait).
+bool pdl_enabled() {
+    static const bool v = [] {
+        const char *e = getenv("SOROBN_B200_PDL");
+        return e ? atoi(e) != 0 : false;
+    }();
+    return v;
+}
+
+template <typename Kernel, typename... Args>
+void sbn_launch(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int N_IN>
 cudaError_t launch_batched_n(const SbnStep &q, int64_t grid, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
     const dim3 g(static_cast<unsigned>(grid)), b(SBN_THREADS);
 #define SBN_CASE(CXV)                                                         \
     case CXV:                                                                 \
-        sbn_step_batched<N_IN, CXV><<<g, b, smem, stream>>>(q);               \
+        sbn_launch(sbn_step_batched<N_IN, CXV>, g, b, smem, stream, q);               \
         break;
     if constexpr (N_IN <= 4) {
         switch (q.cx) {
@@ -647,10 +674,10 @@ cudaError_t launch_batched_n(const SbnStep &q, int64_t grid, cudaStream_t stream
             SBN_CASE(6)
             SBN_CASE(8)
             default:
-                sbn_step_batched<N_IN, 0><<<g, b, smem, stream>>>(q);
+                sbn_launch(sbn_step_batched<N_IN, 0>, g, b, smem, stream, q);
         }
     } else {
-        sbn_step_batched<N_IN, 0><<<g, b, smem, stream>>>(q);
+        sbn_launch(sbn_step_batched<N_IN, 0>, g, b, smem, stream, q);
     }
 #undef SBN_CASE
     return cudaGetLastError();
@@ -696,26 +723,26 @@ cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t gri
     const dim3 g(static_cast<unsigned>(grid)), b(tiled_threads());
     if constexpr (NC > 0) {
         switch (tile) {
-            case 2: sbn_step_tiled<NU, NA, NB, NC, 2, kV, 0><<<g, b, smem, stream>>>(q); break;
-            case 3: sbn_step_tiled<NU, NA, NB, NC, 3, kV, 0><<<g, b, smem, stream>>>(q); break;
-            case 4: sbn_step_tiled<NU, NA, NB, NC, 4, kV, 0><<<g, b, smem, stream>>>(q); break;
-            case 5: sbn_step_tiled<NU, NA, NB, NC, 5, kV, 0><<<g, b, smem, stream>>>(q); break;
+            case 2: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 2, kV, 0>, g, b, smem, stream, q); break;
+            case 3: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 3, kV, 0>, g, b, smem, stream, q); break;
+            case 4: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 4, kV, 0>, g, b, smem, stream, q); break;
+            case 5: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 5, kV, 0>, g, b, smem, stream, q); break;
             default: return cudaErrorInvalidValue;
         }
     } else {
 #define SBN_T(TV)                                                                            \
     case TV:                                                                                 \
-        if (preload && q.cx == TV) sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV><<<g, b, smem, stream>>>(q); \
-        else sbn_step_tiled<NU, NA, NB, 0, TV, kV, 0><<<g, b, smem, stream>>>(q);            \
+        if (preload && q.cx == TV) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV>, g, b, smem, stream, q); \
+        else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, 0>, g, b, smem, stream, q);            \
         break;
         switch (tile) {
             SBN_T(2)
             SBN_T(3)
             SBN_T(5)
             case 4:
-                if (preload && q.cx == 4) sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4><<<g, b, smem, stream>>>(q);
-                else if (preload && q.cx == 8) sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8><<<g, b, smem, stream>>>(q);
-                else sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0><<<g, b, smem, stream>>>(q);
+                if (preload && q.cx == 4) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4>, g, b, smem, stream, q);
+                else if (preload && q.cx == 8) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8>, g, b, smem, stream, q);
+                else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0>, g, b, smem, stream, q);
                 break;
             default: return cudaErrorInvalidValue;
         }
@@ -729,12 +756,12 @@ cudaError_t launch_slab(const SbnStep &q, int tile, int64_t grid, cudaStream_t s
     const size_t smem = (static_cast<size_t>(q.slab_smem_off) + static_cast<size_t>(q.n_slab) * kSlabThreads * kV) * 4;
     const dim3 g(static_cast<unsigned>(grid)), b(kSlabThreads);
     switch (tile) {
-        case 2: sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true><<<g, b, smem, stream>>>(q); break;
-        case 3: sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true><<<g, b, smem, stream>>>(q); break;
-        case 5: sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true><<<g, b, smem, stream>>>(q); break;
+        case 2: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true>, g, b, smem, stream, q); break;
+        case 3: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true>, g, b, smem, stream, q); break;
+        case 5: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true>, g, b, smem, stream, q); break;
         case 4:
-            if (q.cx == 8) sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true><<<g, b, smem, stream>>>(q);
-            else sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true><<<g, b, smem, stream>>>(q);
+            if (q.cx == 8) sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true>, g, b, smem, stream, q);
+            else sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true>, g, b, smem, stream, q);
             break;
         default: return cudaErrorInvalidValue;
     }
@@ -802,8 +829,8 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
     if (st.kind == 0) {
         const int threads = 256;
         const int64_t grid = (st.n_out + threads - 1) / threads;
-        if (P->f64) sbn_step_flat<double><<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
-        else sbn_step_flat<float><<<static_cast<unsigned>(grid), threads, 0, stream>>>(q);
+        if (P->f64) sbn_launch(sbn_step_flat<double>, dim3(static_cast<unsigned>(grid)), dim3(threads), 0, stream, q);
+        else sbn_launch(sbn_step_flat<float>, dim3(static_cast<unsigned>(grid)), dim3(threads), 0, stream, q);
         return cudaGetLastError();
     }
     const int64_t rest = st.n_out / (static_cast<int64_t>(q.n_axes > 0 ? q.card[0] : 1) * (q.n_axes > 1 ? q.card[1] : 1));
@@ -812,14 +839,14 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
     if (P->f64) {
         const dim3 g(static_cast<unsigned>(grid)), b(SBN_THREADS);
         switch (q.n_in) {
-            case 1: sbn_step_batched_f64<1><<<g, b, 0, stream>>>(q); break;
-            case 2: sbn_step_batched_f64<2><<<g, b, 0, stream>>>(q); break;
-            case 3: sbn_step_batched_f64<3><<<g, b, 0, stream>>>(q); break;
-            case 4: sbn_step_batched_f64<4><<<g, b, 0, stream>>>(q); break;
-            case 5: sbn_step_batched_f64<5><<<g, b, 0, stream>>>(q); break;
-            case 6: sbn_step_batched_f64<6><<<g, b, 0, stream>>>(q); break;
-            case 7: sbn_step_batched_f64<7><<<g, b, 0, stream>>>(q); break;
-            case 8: sbn_step_batched_f64<8><<<g, b, 0, stream>>>(q); break;
+            case 1: sbn_launch(sbn_step_batched_f64<1>, g, b, 0, stream, q); break;
+            case 2: sbn_launch(sbn_step_batched_f64<2>, g, b, 0, stream, q); break;
+            case 3: sbn_launch(sbn_step_batched_f64<3>, g, b, 0, stream, q); break;
+            case 4: sbn_launch(sbn_step_batched_f64<4>, g, b, 0, stream, q); break;
+            case 5: sbn_launch(sbn_step_batched_f64<5>, g, b, 0, stream, q); break;
+            case 6: sbn_launch(sbn_step_batched_f64<6>, g, b, 0, stream, q); break;
+            case 7: sbn_launch(sbn_step_batched_f64<7>, g, b, 0, stream, q); break;
+            case 8: sbn_launch(sbn_step_batched_f64<8>, g, b, 0, stream, q); break;
             default: return cudaErrorInvalidValue;
         }
         return cudaGetLastError();

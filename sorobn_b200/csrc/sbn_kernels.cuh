@@ -108,6 +108,14 @@ __device__ __forceinline__ void sbn_mbar_wait(uint64_t *bar, uint32_t phase) {
         : "memory");
 }
 
+// Programmatic dependent launch (opt-in on the host side): let the next kernel of the stream
+// be scheduled as soon as every CTA of this one has started, and do not touch anything a
+// predecessor wrote before it has completed.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void sbn_pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 sbn_mul4(float4 a, float4 b) {
     return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
@@ -127,6 +135,7 @@ template <int N_IN, int CX>
 __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_constant__ SbnStep p) {
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
+    sbn_pdl_entry();
 
     const bool staged = p.smem_floats > 0;
     if (staged) {
@@ -247,6 +256,7 @@ __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched(const __grid_con
 // 2 rows per thread (one 128-bit load), tables read through L1 (no staging).
 template <int N_IN>
 __global__ void __launch_bounds__(SBN_THREADS) sbn_step_batched_f64(const __grid_constant__ SbnStep p) {
+    sbn_pdl_entry();
     const int bblock = blockIdx.x % p.n_bblocks;
     int r = blockIdx.x / p.n_bblocks;  // tile id
     const int b = (bblock * SBN_THREADS + threadIdx.x) * 2;
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
     static_assert(!SLAB || (NA == 1 && NB == 1 && NC == 0 && CX > 0), "slab variant: one A, one B, preload");
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
+    sbn_pdl_entry();
 
     const bool staged = p.smem_floats > 0;
     if (staged) {
@@ -698,6 +709,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
 // launch-latency bound, so they get the reference's own precision and range for free).
 template <typename T>
 __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ SbnStep p) {
+    sbn_pdl_entry();
     const int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (o >= p.n_out) return;
     int off[SBN_MAX_IN];
