@@ -118,6 +118,29 @@ class BayesNet:
         blanket.discard(node)
         return sorted(blanket)
 
+    def impute_many(self, samples: pd.DataFrame, **query_params) -> pd.DataFrame:
+        """Batched `impute` (bayes_net.py:877-908): every missing cell (None / NaN) of `samples`
+        is replaced by the most probable joint value of that row's missing variables given its
+        observed ones.  Rows are grouped by which columns they lack; each group is one
+        `query_many` call, i.e. one device program run over all its rows."""
+        out = samples.copy()
+        missing = samples.isna()
+        patterns = missing.apply(lambda r: tuple(c for c in samples.columns if r[c]), axis=1)
+        for pattern, rows in samples.groupby(patterns, sort=False).groups.items():
+            if not pattern:
+                continue
+            observed = [c for c in samples.columns if c not in pattern]
+            if not observed:
+                raise ValueError("a row with every variable missing cannot be imputed")
+            post = self.query_many(*pattern, events=samples.loc[rows, observed], **query_params)
+            best = post.to_numpy().argmax(axis=1)
+            labels = post.columns  # joint states, variables sorted by name
+            names = list(labels.names)
+            for k, name in enumerate(names):
+                values = labels.get_level_values(k) if len(names) > 1 else labels
+                out.loc[rows, name] = np.asarray(values, dtype=object)[best]
+        return out.infer_objects()
+
     def graphviz(self):
         """The structure as a `graphviz.Digraph` (bayes_net.py:910-929); the module is imported
         here, so it is only needed when this is called."""

@@ -512,3 +512,25 @@ def test_batch_of_unlikely_rows_goes_through_the_batched_float64_program():
     codes = np.stack([rows[v].to_numpy().astype(np.uint8) for v in ev_vars])
     assert np.isnan(engine.Program(plan).run(codes, B)).all()
     assert np.isfinite(engine.Program(plan, f64=True).run(codes, B)).all()
+
+
+def test_impute_many_agrees_with_row_by_row_impute():
+    from sorobn_b200 import examples
+
+    bn = examples.asia(seed=2)
+    full = bn.sample(40)
+    holes = full.astype(object).copy()
+    rng = np.random.default_rng(0)
+    for i in range(len(holes)):
+        for c in rng.choice(holes.columns, size=rng.integers(0, 4), replace=False):
+            holes.loc[i, c] = None
+    filled = bn.impute_many(holes)
+    assert not filled.isna().any().any() and list(filled.columns) == list(holes.columns)
+    for i in range(len(holes)):
+        row = {c: (None if pd.isna(holes.loc[i, c]) else holes.loc[i, c]) for c in holes.columns}
+        if all(v is not None for v in row.values()):
+            assert (filled.loc[i] == full.loc[i]).all()
+            continue
+        want = bn.impute(row)
+        for c in holes.columns:
+            assert filled.loc[i, c] == want[c], (i, c)
