@@ -269,6 +269,8 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed and not dist.is_initialized():
+        # stdout carries the one JSON line; NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     wl = workloads.WORKLOADS[args.workload]()
