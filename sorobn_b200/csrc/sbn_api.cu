@@ -251,7 +251,7 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
                 in.estrides.push_back(sk);
             }
             p += n_elim;
-            if (n_elim == 1) in.sx = in.estrides[0];
+            if (n_elim >= 1) in.sx = in.estrides[0];  // zoff enumerates joint states with this variable fastest
             for (int j = 0; j < n_axes; ++j) {
                 const int sj = w[p + j];
                 if (sj < 0) return fail(SBN_E_INVALID, "step %d input %d: negative stride", s, i);
@@ -541,6 +541,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     q->n_in = static_cast<int32_t>(st.in.size());
     q->n_axes = static_cast<int32_t>(st.cards.size());
     q->cx = st.cx;
+    q->cx_inner = st.ecards.empty() ? 1 : st.ecards[0];
     q->zoff = st.zoff_pos >= 0 ? P->d_tile_off + st.zoff_pos : nullptr;
     if (st.kind == 1 && st.tile > 0 && P->use_tiled && !P->f64 && st.zoff_tiled_pos >= 0) q->zoff = P->d_tile_off + st.zoff_tiled_pos;
     q->n_out = static_cast<int32_t>(st.n_out);
@@ -732,7 +733,9 @@ cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t gri
     } else {
 #define SBN_T(TV)                                                                            \
     case TV:                                                                                 \
-        if (preload && q.cx == TV) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV>, g, b, smem, stream, q); \
+        if (preload && q.cx == TV && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV>, g, b, smem, stream, q); \
+        else if (preload && q.cx_inner == TV && q.zoff != nullptr)                                                  \
+            sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV, false, true>, g, b, smem, stream, q);                  \
         else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, 0>, g, b, smem, stream, q);            \
         break;
         switch (tile) {
@@ -740,8 +743,10 @@ cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t gri
             SBN_T(3)
             SBN_T(5)
             case 4:
-                if (preload && q.cx == 4) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4>, g, b, smem, stream, q);
-                else if (preload && q.cx == 8) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8>, g, b, smem, stream, q);
+                if (preload && q.cx == 4 && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4>, g, b, smem, stream, q);
+                else if (preload && q.cx == 8 && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8>, g, b, smem, stream, q);
+                else if (preload && q.cx_inner == 4 && q.zoff != nullptr)
+                    sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4, false, true>, g, b, smem, stream, q);
                 else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0>, g, b, smem, stream, q);
                 break;
             default: return cudaErrorInvalidValue;
@@ -782,9 +787,9 @@ cudaError_t set_slab_attr() {
 cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int64_t grid, cudaStream_t stream) {
     if (q.slab_off != nullptr) return st.nu == 0 ? launch_slab<0>(q, st.tile, grid, stream) : launch_slab<1>(q, st.tile, grid, stream);
     const int key = st.nu * 1000 + st.na * 100 + st.nb * 10 + st.nc;
-    // the preload schedule keeps every operand of a tile in registers: only for <= 3 inputs,
-    // one eliminated variable
-    preload = preload && st.in.size() <= 3 && q.zoff == nullptr;
+    // the preload schedule keeps every operand of a tile, for one block of eliminated states, in
+    // registers: only for <= 3 inputs
+    preload = preload && st.in.size() <= 3;
     switch (key) {
 #define X(U, A, B, C) \
     case U * 1000 + A * 100 + B * 10 + C: return launch_tiled_c<U, A, B, C>(q, st.tile, preload, grid, stream);
@@ -803,6 +808,10 @@ cudaError_t set_tiled_attr_c() {
     SBN_A(2, 0) SBN_A(3, 0) SBN_A(4, 0) SBN_A(5, 0)
     if constexpr (NC == 0) {
         SBN_A(2, 2) SBN_A(3, 3) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 5)
+#define SBN_AM(TV) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, TV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+        SBN_AM(2) SBN_AM(3) SBN_AM(4) SBN_AM(5)
+#undef SBN_AM
     }
 #undef SBN_A
     return e;

@@ -67,7 +67,7 @@ struct SbnStep {
     int32_t n_slab;                   // cx * slab_ma
     int32_t slab_ma;                  // A-side entries per eliminated state in one slab
     int32_t slab_smem_off;            // float offset of the slab inside dynamic shared memory
-    int32_t pad2_;
+    int32_t cx_inner;                 // states of the FIRST eliminated variable (block of the preload schedule)
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -381,7 +381,8 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 // (the kernel is latency-bound otherwise: ~16 warps per SM because of the accumulators).
 // With a C-side input (T*T loads per x already) only the x-loop schedule is built.
 // When several variables are eliminated at once, x runs over their joint states and the
-// per-input element offset comes from `zoff` instead of x * sx.
+// per-input element offset comes from `zoff` instead of x * sx; the preload schedule then
+// preloads one block of CX states (the first eliminated variable) per joint state of the rest.
 //
 // SLAB = true is the variant for *expanding* products (both the A-side and the B-side batched
 // factor have private axes beyond the tile, e.g. 3125 <- B625 x B625): every A entry is needed
@@ -391,8 +392,8 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 // barrier: a thread only ever reads back what it wrote), then walks the group's tiles reading
 // A from shared memory and B blocks through registers (reloaded only when the block
 // changes).  Both factors are then read from HBM exactly once.
-template <int NU, int NA, int NB, int NC, int T, int V, int CX, bool SLAB = false>
-__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 : 4)))
+template <int NU, int NA, int NB, int NC, int T, int V, int CX, bool SLAB = false, bool MX = false>
+__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA + NB + NC <= 2) ? 3 : 2) : (NC > 0 ? 3 : 4)))
     sbn_step_tiled(const __grid_constant__ SbnStep p) {
     constexpr int N_IN = NU + NA + NB + NC;
     constexpr int TB = (NB > 0 || NC > 0) ? T : 1;  // no input with axis 1: single-axis output
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
     static_assert(NC <= 1, "one input may span both tile axes");
     static_assert(CX == 0 || NC == 0, "the preload schedule does not cover a C-side input");
     static_assert(!SLAB || (NA == 1 && NB == 1 && NC == 0 && CX > 0), "slab variant: one A, one B, preload");
+    static_assert(!MX || (CX > 0 && !SLAB), "MX: several eliminated variables on the preload schedule");
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
     sbn_pdl_entry();
@@ -528,6 +530,14 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
             for (int d = 0; d < TB; ++d) k1[d] = FULL ? d : min(d, nb - 1);
 
             if constexpr (CX > 0) {
+              // Several eliminated variables: the first one (CX states, stride sx) is the block
+              // that is preloaded, the joint states of the others are walked by `xo` with their
+              // offsets from zoff -- the accumulators stay in registers across blocks.
+              // (MX = false: one variable, one block -- the loop and the offsets fold away)
+              for (int xo = 0; xo < (MX ? cx : 1); xo += CX) {
+                int ob[N_IN];
+#pragma unroll
+                for (int i = 0; i < N_IN; ++i) ob[i] = MX ? base[i] + __ldg(p.zoff + i * cx + xo) : base[i];
                 // ---- preload schedule: all loads first ...
                 float ra[NA > 0 ? NA : 1][CX][T][V], rb[NB > 0 ? NB : 1][CX][TB][V], ru[NU > 0 ? NU : 1][CX][V];
                 if constexpr (SLAB) {
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
 #pragma unroll
                         for (int x = 0; x < CX; ++x)
 #pragma unroll
-                            for (int d = 0; d < T; ++d) fetch(i, base[i] + x * sx + k0[d] * s0, ra[j][x][d]);
+                            for (int d = 0; d < T; ++d) fetch(i, ob[i] + x * sx + k0[d] * s0, ra[j][x][d]);
                     }
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
@@ -571,14 +581,14 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
 #pragma unroll
                         for (int x = 0; x < CX; ++x)
 #pragma unroll
-                            for (int d = 0; d < TB; ++d) fetch(i, base[i] + x * sx + k1[d] * s1, rb[j][x][d]);
+                            for (int d = 0; d < TB; ++d) fetch(i, ob[i] + x * sx + k1[d] * s1, rb[j][x][d]);
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
                     const int sx = p.in[i].sx;
 #pragma unroll
-                    for (int x = 0; x < CX; ++x) fetch(i, base[i] + x * sx, ru[i][x]);
+                    for (int x = 0; x < CX; ++x) fetch(i, ob[i] + x * sx, ru[i][x]);
                 }
                 // ---- ... then the arithmetic
 #pragma unroll
@@ -611,6 +621,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? 2 : (NC > 0 ? 3 :
 #pragma unroll
                             for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
                 }
+              }
             } else {
 #pragma unroll 2
                 for (int x = 0; x < cx; ++x) {

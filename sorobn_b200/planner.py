@@ -246,7 +246,7 @@ def table_scale_log2(table: np.ndarray) -> int:
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
-               merge_sum_outs=None, lift_evidence=True, allow_empty_query=False) -> Plan:
+               merge_sum_outs=None, lift_evidence=True, allow_empty_query=False, fuse_elims=None) -> Plan:
     """Plan P(query | evidence) for `net`.
 
     query / evidence are sequences of var ids.  `evidence` fixes the evidence
@@ -254,6 +254,8 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     """
     if merge_sum_outs is None:
         merge_sum_outs = os.environ.get("SOROBN_B200_MERGE", "0") == "1"
+    if fuse_elims is None:
+        fuse_elims = os.environ.get("SOROBN_B200_FUSE", "1") == "1"
     query = tuple(query)
     evidence = tuple(evidence)
     if not query and not allow_empty_query:
@@ -322,6 +324,8 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         launch; consumers gather from it like from a CPT.  The reference filters every CPT by
         the event first (bayes_net.py:772-774); filtering after multiplying gives the same
         numbers and turns per-row work into per-call work."""
+        elims = () if elim is None else (tuple(elim) if isinstance(elim, (tuple, list)) else (elim,))
+        ecards = tuple(int(card[e]) for e in elims)
         dep = any(f.depends_on_evidence for f in inputs)
         batched = dep and mode == MODE_BATCHED
         if len(out_vars) > MAX_AXES:
@@ -352,11 +356,10 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
             for f in inputs:
                 pos = {u: sd for u, sd in zip(f.vars, f.strides)}
                 pos.update({evidence[col]: sd for col, sd, _ in f.ev})
-                es = (pos.get(elim, 0),) if elim is not None else ()
+                es = tuple(pos.get(e, 0) for e in elims)
                 plain = _Factor(f.is_slot, f.buf, f.vars, f.strides, (), False)  # evidence axes are output axes here
                 ins.append((plain, es, tuple(pos.get(u, 0) for u in axes)))
-            steps.append(Step(KIND_FLAT, ins, out_id, axes, axis_cards,
-                              (elim,) if elim is not None else (), (int(card[elim]),) if elim is not None else ()))
+            steps.append(Step(KIND_FLAT, ins, out_id, axes, axis_cards, elims, ecards))
             strides, acc = [], 1
             for c in axis_cards:
                 strides.append(acc)
@@ -367,10 +370,9 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
 
         for f in inputs:
             pos = {u: s for u, s in zip(f.vars, f.strides)}
-            es = (pos.get(elim, 0),) if elim is not None else ()
+            es = tuple(pos.get(e, 0) for e in elims)
             ins.append((f, es, tuple(pos.get(u, 0) for u in out_vars)))
-        steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_id, tuple(out_vars), cards,
-                          (elim,) if elim is not None else (), (int(card[elim]),) if elim is not None else ()))
+        steps.append(Step(KIND_BATCHED if batched else KIND_FLAT, ins, out_id, tuple(out_vars), cards, elims, ecards))
         out_strides = []
         acc = 1
         for c in cards:
@@ -454,14 +456,35 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         if final_vars is not None:
             assert union == set(final_vars), (union, final_vars)
             return emit(inputs, None, list(final_vars), may_lift=False)
-        out_set = union - {elim}
-        return emit(inputs, elim, axis_order(inputs, out_set))
+        elims = () if elim is None else (tuple(elim) if isinstance(elim, (tuple, list)) else (elim,))
+        out_set = union - set(elims)
+        return emit(inputs, elims if elims else None, axis_order(inputs, out_set))
 
     # bayes_net.py:778-786
-    for x in order:
+    # A later variable of the order whose every factor is already in x's bucket is summed out by
+    # the same launch: sum_w sum_x prod(bucket).  Same multiplies, but the intermediate over w is
+    # never written and read back, and the tile axes are chosen for the launch's real output.
+    gone = set()
+    for k, x in enumerate(order):
+        if x in gone:
+            continue
         touching = [f for f in factors if x in f.vars]
         factors = [f for f in factors if x not in f.vars]
-        factors.append(product_chain(touching, x))
+        elims = [x]
+        if fuse_elims and mode == MODE_BATCHED and any(f.depends_on_evidence for f in touching):
+            union = set().union(*[f.vars for f in touching])
+            z = int(card[x])
+            for w in order[k + 1:]:
+                if len(elims) >= MAX_ELIM:
+                    break
+                if w in gone or w not in union or any(w in f.vars for f in factors):
+                    continue
+                if z * int(card[w]) > MAX_Z:
+                    continue
+                elims.append(w)
+                z *= int(card[w])
+        gone.update(elims)
+        factors.append(product_chain(touching, tuple(elims)))
 
     # bayes_net.py:788-794: product of what is left; the answer's levels are sorted
     # by name (bayes_net.py:872-873) and rows by state (sort_index, :875)
