@@ -788,8 +788,8 @@ cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int
     if (q.slab_off != nullptr) return st.nu == 0 ? launch_slab<0>(q, st.tile, grid, stream) : launch_slab<1>(q, st.tile, grid, stream);
     const int key = st.nu * 1000 + st.na * 100 + st.nb * 10 + st.nc;
     // the preload schedule keeps every operand of a tile, for one block of eliminated states, in
-    // registers: only for <= 3 inputs
-    preload = preload && st.in.size() <= 3;
+    // registers: only for <= 3 inputs, or 4 when two of them carry no tile axis (one value per state)
+    preload = preload && (st.in.size() <= 3 || (st.nu == 2 && st.na == 1 && st.nb == 1));
     switch (key) {
 #define X(U, A, B, C) \
     case U * 1000 + A * 100 + B * 10 + C: return launch_tiled_c<U, A, B, C>(q, st.tile, preload, grid, stream);

@@ -65,6 +65,7 @@ MAX_Z = 256  # joint states of the variables summed out by one launch
 # ends up gathering from a 62 KB table for every output).
 LIFT_MAX = int(os.environ.get("SOROBN_B200_LIFT_MAX", "4096"))
 TILED_MAX_IN = 4  # inputs of one launch of the tiled kernel (csrc: kTiledMaxIn)
+PRELOAD_MAX_IN = 3  # the tiled kernel's preload schedule (all operands of a block in registers)
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
 HEADER_WORDS = 12
@@ -419,7 +420,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         cols = {(col, c) for f in fs for col, _, c in f.ev}
         return int(np.prod([card[u] for u in vs], dtype=np.int64)) * int(np.prod([c for _, c in cols], dtype=np.int64))
 
-    def combine_tables(inputs):
+    def combine_tables(inputs, limit=TILED_MAX_IN):
         """A launch with more than TILED_MAX_IN factors falls off the tiled kernel.  When the
         surplus is small tables, multiply those together first: a table-only product is an
         evidence-independent flat launch (see `emit`), and the big launch then gathers one
@@ -427,7 +428,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         inputs = list(inputs)
         if mode != MODE_BATCHED or not lift_evidence:
             return inputs
-        while len(inputs) > TILED_MAX_IN:
+        while len(inputs) > limit:
             tabs = [f for f in inputs if not f.batched]
             best = None
             for i in range(len(tabs)):
@@ -444,7 +445,9 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         return inputs
 
     def product_chain(inputs, elim, final_vars=None):
-        inputs = combine_tables(inputs)
+        # a launch that sums out several variables keeps to the preload schedule's 3 inputs
+        fused = isinstance(elim, (tuple, list)) and len(elim) > 1
+        inputs = combine_tables(inputs, PRELOAD_MAX_IN if fused else TILED_MAX_IN)
         # bayes_net.py:256 reduces pairwise; fuse up to max_in factors per launch and
         # fold the smallest ones first when there are more
         while len(inputs) > max_in:
@@ -461,9 +464,11 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         return emit(inputs, elims if elims else None, axis_order(inputs, out_set))
 
     # bayes_net.py:778-786
-    # A later variable of the order whose every factor is already in x's bucket is summed out by
-    # the same launch: sum_w sum_x prod(bucket).  Same multiplies, but the intermediate over w is
-    # never written and read back, and the tile axes are chosen for the launch's real output.
+    # Fused eliminations.  A later variable w of the order joins x's launch when every factor
+    # that mentions w is in x's bucket already, or is a table over variables the bucket covers
+    # anyway: sum_w sum_x prod(bucket + those tables).  The joint state space is the one the
+    # separate launches walk, but the intermediate over w is never written and read back, and
+    # the tile axes are chosen for the launch's real output.
     gone = set()
     for k, x in enumerate(order):
         if x in gone:
@@ -471,16 +476,21 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         touching = [f for f in factors if x in f.vars]
         factors = [f for f in factors if x not in f.vars]
         elims = [x]
-        if fuse_elims and mode == MODE_BATCHED and any(f.depends_on_evidence for f in touching):
+        if fuse_elims and mode == MODE_BATCHED and any(f.batched for f in touching):
             union = set().union(*[f.vars for f in touching])
             z = int(card[x])
             for w in order[k + 1:]:
                 if len(elims) >= MAX_ELIM:
                     break
-                if w in gone or w not in union or any(w in f.vars for f in factors):
+                if w in gone or w not in union or z * int(card[w]) > MAX_Z:
                     continue
-                if z * int(card[w]) > MAX_Z:
+                extra = [f for f in factors if w in f.vars]
+                if any(f.batched or not set(f.vars) <= union for f in extra):
                     continue
+                if extra and len(touching) + len(extra) > TILED_MAX_IN:
+                    continue
+                touching += extra
+                factors = [f for f in factors if w not in f.vars]
                 elims.append(w)
                 z *= int(card[w])
         gone.update(elims)
