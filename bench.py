@@ -269,9 +269,19 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed and not dist.is_initialized():
-        # stdout carries the one JSON line; NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line: NCCL prints its version banner to fd 1 when the
+        # communicator is created, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     wl = workloads.WORKLOADS[args.workload]()
     bn = wl.build(device=local_rank)
