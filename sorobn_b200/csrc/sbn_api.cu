@@ -76,6 +76,7 @@ struct StepDesc {
     int64_t tile_off_pos = 0;  // int32 offset into sbn_program::d_tile_off
     // slab variant (expanding products): tiles grouped by the digits A and B share
     bool slab = false;
+    bool big_tables = false;     // staged tables exceed SBN_SMEM_BUDGET: one CTA per SM (see smem_big)
     int slab_ma = 0, n_slab = 0;
     int64_t slab_off_pos = 0;
     int64_t slab_tile_off_pos = 0;  // tile table in slab order (rows of n_in + 5 words)
@@ -285,6 +286,19 @@ int tiled_threads() {
 }
 
 constexpr int kSlabThreads = 64;                 // CTA size of the slab variant (x kRowsPerThread rows)
+// Tables staged per CTA: SBN_SMEM_BUDGET keeps several CTAs per SM.  Opt-in experiment
+// (SOROBN_B200_SMEM_BIG=<KB>, up to 200): a launch around a larger CPT (8^5 entries = 128 KB) stages
+// it with ONE CTA per SM walking every tile of its rows.  Measured on dag50: no gain (4 warps per
+// SM are latency-bound on the shared-memory gathers: 2.65 vs 2.13 ms and 2.03 vs 2.21 ms on the two
+// launches it applies to), so the default leaves such tables to the L1/L2 gathers of the plain kernel.
+int64_t smem_big() {
+    static const int64_t v = [] {
+        const char *e = getenv("SOROBN_B200_SMEM_BIG");
+        const int64_t kb = e ? atoll(e) : SBN_SMEM_BUDGET / 1024;
+        return std::max<int64_t>(SBN_SMEM_BUDGET, std::min<int64_t>(kb * 1024, SBN_SMEM_BIG));
+    }();
+    return v;
+}
 constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one slab may take
 
 // Slab variant of the tiled kernel: eligible when the launch multiplies one batched factor on
@@ -409,7 +423,8 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         int64_t smem = 0;
         for (const InDesc &in : st.in)
             if (!in.batched) smem += in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
-        if (smem * 4 > SBN_SMEM_BUDGET) continue;
+        if (smem * 4 > smem_big()) continue;
+        st.big_tables = smem * 4 > SBN_SMEM_BUDGET;
         const int n_axes = static_cast<int>(st.cards.size());
         const int c0 = n_axes > 0 ? st.cards[0] : 1;
         const int c1 = n_axes > 1 ? st.cards[1] : 1;
@@ -571,7 +586,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         for (size_t j = 0; j < in.strides.size(); ++j) d.stride[j] = in.strides[j];
         d.smem_off = -1;
         d.stage_floats = 0;
-        if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= SBN_SMEM_BUDGET) {
+        if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= (tiled ? smem_big() : SBN_SMEM_BUDGET)) {
             d.smem_off = smem;
             d.stage_floats = static_cast<int32_t>(padded);
             smem += static_cast<int>(padded);
@@ -588,7 +603,8 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
             return e ? atoll(e) : 0LL;
         }();
         // swept on B200 (grid workload): 3552 -> 4.20 ms, 7104 -> 4.10 ms, 14208 -> 4.23 ms
-        const int64_t target = target_env > 0 ? target_env : 8 * 148 * 6;
+        // big tables: one CTA per SM, so few CTAs that each amortise their 100+ KB of staging
+        const int64_t target = st.big_tables ? 4 * 148 : (target_env > 0 ? target_env : 8 * 148 * 6);
         int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(st.n_tiles, target / std::max<int64_t>(1, n_rblocks)));
         int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
         q->tiles_per_cta = static_cast<int32_t>(tpc);
@@ -598,7 +614,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         q->n_bblocks = static_cast<int32_t>(n_rblocks);
         q->tile1 = 0;
         q->n_tile1 = 0;
-        if (st.slab && P->use_preload && P->use_slab) {
+        if (st.slab && !st.big_tables && P->use_preload && P->use_slab) {
             // whole groups per CTA; 64-thread CTAs (128 rows) so that the slab fits shared memory
             const int64_t rows_slab = static_cast<int64_t>(kSlabThreads) * kRowsPerThread;
             const int64_t n_rb = (n_rows + rows_slab - 1) / rows_slab;
@@ -804,12 +820,12 @@ template <int NU, int NA, int NB, int NC>
 cudaError_t set_tiled_attr_c() {
     cudaError_t e = cudaSuccess;
 #define SBN_A(TV, CXV) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
     SBN_A(2, 0) SBN_A(3, 0) SBN_A(4, 0) SBN_A(5, 0)
     if constexpr (NC == 0) {
         SBN_A(2, 2) SBN_A(3, 3) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 5)
 #define SBN_AM(TV) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, TV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, TV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
         SBN_AM(2) SBN_AM(3) SBN_AM(4) SBN_AM(5)
 #undef SBN_AM
     }

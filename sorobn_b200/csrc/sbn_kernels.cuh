@@ -26,7 +26,8 @@
 
 #define SBN_THREADS 128      // threads per CTA of the batched kernel (4 rows each)
 #define SBN_ROWS_PER_CTA (SBN_THREADS * 4)
-#define SBN_SMEM_BUDGET (64 * 1024)
+#define SBN_SMEM_BUDGET (64 * 1024)   // staged tables of an ordinary launch (several CTAs per SM)
+#define SBN_SMEM_BIG (200 * 1024)     // ... of a launch around one big CPT: one CTA per SM
 
 struct SbnInput {
     const float *ptr;                // table / slot base (device)
