@@ -81,6 +81,11 @@ struct StepDesc {
     int64_t slab_off_pos = 0;
     int64_t slab_tile_off_pos = 0;  // tile table in slab order (rows of n_in + 5 words)
     int64_t tiles_per_super = 0, n_super = 0;
+    // sliced staging (tables beyond SBN_SMEM_BUDGET): per chunk of `slice_tpc` tiles, per input,
+    // (first float, floats, shared-memory offset) of the part of the table those tiles touch
+    int64_t slice_pos = -1;
+    int64_t slice_tpc = 0;
+    int64_t slice_smem = 0;      // floats of shared memory of the largest chunk
 };
 struct Slot {
     bool batched;
@@ -307,6 +312,70 @@ constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one s
 // B-private digits and B blocks, then the A-private digits and A blocks) and the slab's entry
 // offsets.  Returns false when the step does not qualify (the caller then emits the plain
 // tile table).
+// Sliced staging.  The planner ships a CPT that is too big for shared memory with the output
+// axes >= 2 outermost (planner.py `_relayout_big_tables`), so the tiles of one chunk touch a
+// contiguous part of it.  Find the largest chunk whose parts fit SBN_SMEM_BUDGET and record, per
+// chunk and input, which floats to stage and where.
+int64_t slice_budget() {
+    static const int64_t v = [] {
+        const char *e = getenv("SOROBN_B200_SLICE_KB");
+        const int64_t kb = e ? atoll(e) : SBN_SMEM_BUDGET / 1024;
+        return std::max<int64_t>(1024, std::min<int64_t>(kb * 1024, SBN_SMEM_BUDGET));
+    }();
+    return v;
+}
+bool plan_slices(sbn_program *P, StepDesc &st, int T, std::vector<int32_t> *words) {
+    const int n_in = static_cast<int>(st.in.size());
+    const int n_axes = static_cast<int>(st.cards.size());
+    const int row_words = n_in + 2;
+    std::vector<int64_t> span(n_in, 0), size(n_in, 0);
+    for (int i = 0; i < n_in; ++i) {
+        const InDesc &in = st.in[st.order[i]];
+        if (in.batched) continue;
+        size[i] = in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
+        int64_t sp = 0;
+        for (size_t k = 0; k < st.ecards.size(); ++k) sp += static_cast<int64_t>(st.ecards[k] - 1) * in.estrides[k];
+        if (n_axes > 0) sp += static_cast<int64_t>(std::min(T, st.cards[0]) - 1) * in.strides[0];
+        if (n_axes > 1) sp += static_cast<int64_t>(std::min(T, st.cards[1]) - 1) * in.strides[1];
+        for (const EvAxis &a : in.ev) sp += static_cast<int64_t>(a.card - 1) * a.stride;
+        span[i] = sp;
+    }
+    for (int64_t tpc = st.n_tiles; tpc >= 1; tpc = (tpc == 1 ? 0 : (tpc + 1) / 2)) {
+        const int64_t chunks = (st.n_tiles + tpc - 1) / tpc;
+        std::vector<int32_t> rec;
+        rec.reserve(static_cast<size_t>(chunks) * n_in * 3);
+        int64_t worst = 0;
+        for (int64_t c = 0; c < chunks; ++c) {
+            int64_t smem = 0;
+            for (int i = 0; i < n_in; ++i) {
+                if (st.in[st.order[i]].batched) {
+                    rec.insert(rec.end(), {0, 0, -1});
+                    continue;
+                }
+                int64_t lo = INT64_MAX, hi = 0;
+                for (int64_t t = c * tpc; t < std::min(st.n_tiles, (c + 1) * tpc); ++t) {
+                    const int64_t base = (*words)[static_cast<size_t>(st.tile_off_pos + t * row_words + 2 + i)];
+                    lo = std::min(lo, base);
+                    hi = std::max(hi, base + span[i] + 1);
+                }
+                lo = lo / 4 * 4;
+                const int64_t len = std::min(round_up(hi - lo, 4), size[i] - lo);
+                rec.insert(rec.end(), {static_cast<int32_t>(lo), static_cast<int32_t>(len), static_cast<int32_t>(smem)});
+                smem += len;
+            }
+            worst = std::max(worst, smem);
+        }
+        if (worst * 4 <= slice_budget()) {
+            st.slice_pos = static_cast<int64_t>(words->size());
+            words->insert(words->end(), rec.begin(), rec.end());
+            st.slice_tpc = tpc;
+            st.slice_smem = worst;
+            return true;
+        }
+    }
+    return false;
+}
+
 bool plan_slab(sbn_program *P, StepDesc &st, int T, std::vector<int32_t> *words) {
     (void)P;
     const int n_axes = static_cast<int>(st.cards.size());
@@ -423,8 +492,9 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         int64_t smem = 0;
         for (const InDesc &in : st.in)
             if (!in.batched) smem += in.is_slot ? P->slots[in.id].padded : P->table_padded[in.id];
-        if (smem * 4 > smem_big()) continue;
-        st.big_tables = smem * 4 > SBN_SMEM_BUDGET;
+        const bool over = smem * 4 > SBN_SMEM_BUDGET;
+        st.big_tables = over && smem * 4 <= smem_big();
+        const bool sliced = over && !st.big_tables;  // decided below, once the tiles are known
         const int n_axes = static_cast<int>(st.cards.size());
         const int c0 = n_axes > 0 ? st.cards[0] : 1;
         const int c1 = n_axes > 1 ? st.cards[1] : 1;
@@ -492,7 +562,7 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
         st.tile = T;
         st.n_tiles = n_tiles;
         st.slab = false;
-        plan_slab(P, st, T, words);  // optional second tile table in slab order
+        if (!over) plan_slab(P, st, T, words);  // optional second tile table in slab order
         st.tile_off_pos = static_cast<int64_t>(words->size());
         std::vector<int64_t> off(n_in);
         for (int64_t r = 0; r < rest; ++r) {
@@ -517,6 +587,7 @@ void plan_tiles(sbn_program *P, std::vector<int32_t> *words) {
                 }
             }
         }
+        if (sliced && !plan_slices(P, st, T, words)) st.tile = 0;  // plain kernel, tables from L1/L2
     }
 }
 
@@ -586,13 +657,21 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         for (size_t j = 0; j < in.strides.size(); ++j) d.stride[j] = in.strides[j];
         d.smem_off = -1;
         d.stage_floats = 0;
-        if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= (tiled ? smem_big() : SBN_SMEM_BUDGET)) {
+        if (tiled && st.slice_pos >= 0) {
+            // sliced staging: the kernel reads (first float, floats, offset) per chunk from q->slices
+            if (!in.batched) d.smem_off = 0;
+        } else if (st.kind == 1 && !P->f64 && !in.batched && (smem + padded) * 4 <= (tiled ? smem_big() : SBN_SMEM_BUDGET)) {
             d.smem_off = smem;
             d.stage_floats = static_cast<int32_t>(padded);
             smem += static_cast<int>(padded);
         }
     }
     q->smem_floats = smem;
+    q->slices = nullptr;
+    if (tiled && st.slice_pos >= 0) {
+        q->smem_floats = static_cast<int32_t>(st.slice_smem);
+        q->slices = P->d_tile_off + st.slice_pos;
+    }
     if (tiled) {
         const int64_t rows_per_cta = static_cast<int64_t>(tiled_threads()) * kRowsPerThread;
         const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
@@ -607,6 +686,7 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         const int64_t target = st.big_tables ? 4 * 148 : (target_env > 0 ? target_env : 8 * 148 * 6);
         int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(st.n_tiles, target / std::max<int64_t>(1, n_rblocks)));
         int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
+        if (st.slice_pos >= 0) tpc = st.slice_tpc;  // the slices were cut for this chunk size
         q->tiles_per_cta = static_cast<int32_t>(tpc);
         q->n_tiles = static_cast<int32_t>(st.n_tiles);
         q->n_chunks = static_cast<int32_t>((st.n_tiles + tpc - 1) / tpc);

@@ -69,6 +69,7 @@ struct SbnStep {
     int32_t slab_ma;                  // A-side entries per eliminated state in one slab
     int32_t slab_smem_off;            // float offset of the slab inside dynamic shared memory
     int32_t cx_inner;                 // states of the FIRST eliminated variable (block of the preload schedule)
+    const int32_t *slices;            // sliced staging: [n_chunks][n_in][3] = first float, floats, smem offset
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -407,6 +408,16 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA +
     __shared__ __align__(8) uint64_t s_bar;
     sbn_pdl_entry();
 
+    // Tile chunks vary fastest: the CTAs resident at any moment then cover all tiles of a
+    // few row blocks, so operands shared between tiles are re-read from L2, not from HBM.
+    const int rblock = blockIdx.x / p.n_chunks;
+    const int chunk = blockIdx.x % p.n_chunks;
+
+    // Tables are staged whole, or -- when they are too big -- only the part this chunk's tiles
+    // touch (p.slices; the planner lays such a table out so that the part is contiguous).
+    int tab_off[N_IN];  // shared-memory float offset of element 0 of table i (may be negative)
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) tab_off[i] = p.in[i].smem_off;
     const bool staged = p.smem_floats > 0;
     if (staged) {
         if (threadIdx.x == 0) {
@@ -414,7 +425,25 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA +
             sbn_fence_mbar_init();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (p.slices) {
+            const int32_t *sl = p.slices + static_cast<int64_t>(chunk) * (N_IN * 3);
+            uint32_t total = 0;
+#pragma unroll
+            for (int i = 0; i < N_IN; ++i) {
+                tab_off[i] = __ldg(sl + i * 3 + 2) - __ldg(sl + i * 3);
+                total += static_cast<uint32_t>(__ldg(sl + i * 3 + 1)) * 4u;
+            }
+            if (threadIdx.x == 0) {
+                sbn_mbar_expect_tx(&s_bar, total);
+#pragma unroll
+                for (int i = 0; i < N_IN; ++i) {
+                    const int len = __ldg(sl + i * 3 + 1);
+                    if (len > 0)
+                        sbn_tma_bulk_g2s(s_tab + __ldg(sl + i * 3 + 2), p.in[i].ptr + __ldg(sl + i * 3),
+                                         static_cast<uint32_t>(len) * 4u, &s_bar);
+                }
+            }
+        } else if (threadIdx.x == 0) {
             sbn_mbar_expect_tx(&s_bar, static_cast<uint32_t>(p.smem_floats) * 4u);
 #pragma unroll
             for (int i = 0; i < N_IN; ++i) {
@@ -426,10 +455,6 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA +
         }
     }
 
-    // Tile chunks vary fastest: the CTAs resident at any moment then cover all tiles of a
-    // few row blocks, so operands shared between tiles are re-read from L2, not from HBM.
-    const int rblock = blockIdx.x / p.n_chunks;
-    const int chunk = blockIdx.x % p.n_chunks;
     const int b = (rblock * static_cast<int>(blockDim.x) + threadIdx.x) * V;
     const bool live = b < p.n_rows;  // b % V == 0 and ld % 32 == 0: the vector stays inside the pitch
 
@@ -439,7 +464,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA +
     for (int i = 0; i < N_IN; ++i) {
         gsrc[i] = p.in[i].ptr + b;
 #pragma unroll
-        for (int l = 0; l < V; ++l) evo[i][l] = p.in[i].smem_off;
+        for (int l = 0; l < V; ++l) evo[i][l] = tab_off[i];
         if (!p.in[i].batched && live) {
             for (int k = 0; k < p.in[i].n_ev; ++k) {
                 const uint8_t *col = p.ev + static_cast<int64_t>(p.in[i].ev_col[k]) * p.ld_ev + b;

@@ -65,6 +65,7 @@ MAX_Z = 256  # joint states of the variables summed out by one launch
 # ends up gathering from a 62 KB table for every output).
 LIFT_MAX = int(os.environ.get("SOROBN_B200_LIFT_MAX", "4096"))
 TILED_MAX_IN = 4  # inputs of one launch of the tiled kernel (csrc: kTiledMaxIn)
+SLICE_MIN_BYTES = 64 * 1024  # tables of one launch beyond this are laid out for sliced staging (csrc: SBN_SMEM_BUDGET)
 PRELOAD_MAX_IN = 3  # the tiled kernel's preload schedule (all operands of a block in registers)
 MODE_FLAT, MODE_BATCHED = 0, 1
 KIND_FLAT, KIND_BATCHED = 0, 1
@@ -286,6 +287,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     tables = sorted(relevant)
     factors = []
     table_arrays = []
+    table_axes = []  # variable of every axis of table_arrays[t], outermost first
     for t, v in enumerate(tables):
         scope = net.scope(v)
         # Shipped layout: free axes first (reference order), evidence axes innermost.  Rows of
@@ -295,6 +297,7 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
         arr = np.ascontiguousarray(np.transpose(net.cpt[v], perm))
         table_arrays.append(arr)
         pscope = [scope[i] for i in perm]
+        table_axes.append(list(pscope))
         shape = [int(card[u]) for u in pscope]
         strides = [int(np.prod(shape[i + 1:], dtype=np.int64)) for i in range(len(shape))]
         free = [(u, s) for u, s in zip(pscope, strides) if u not in ev_col]
@@ -503,6 +506,8 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     Q = fsize(post)
 
     steps = _merge_sum_outs(steps, merge_sum_outs)
+    if mode == MODE_BATCHED:
+        _relayout_big_tables(steps, table_arrays, table_axes, evidence, card)
     slots, post_slot = _assign_slots(steps, post.buf)
 
     plan = Plan(mode=mode, query=q_sorted, evidence=evidence, order=list(order), tables=tables,
@@ -511,6 +516,47 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     plan._card = card
     _serialise(plan, table_arrays)
     return plan
+
+
+def _relayout_big_tables(steps, table_arrays, table_axes, evidence, card):
+    """Lay a big CPT out for its (single) consumer.
+
+    A launch stages its tables in shared memory; a CPT that does not fit (SLICE_MIN_BYTES: the
+    engine's 64 KB budget) can still be staged slice by slice when the tiles one CTA walks touch
+    a contiguous part of it.  Tiles enumerate the output axes >= 2 (axis 2 fastest), so the table
+    is shipped with those axes outermost in the same significance order, then the eliminated
+    variables, then the two tile axes, then its evidence axes (innermost, as for every table).
+    Every CPT enters exactly one launch, so nobody else sees the new layout."""
+    for st in steps:
+        if st.kind != KIND_BATCHED:
+            continue
+        tabs = [k for k, (f, _, _) in enumerate(st.inputs) if not f.is_slot]
+        total = sum(table_arrays[st.inputs[k][0].buf].size for k in tabs) * 4
+        if total <= SLICE_MIN_BYTES:
+            continue
+        rank = {}  # variable -> significance (higher = outer)
+        for j, u in enumerate(st.out_vars):
+            rank[u] = (0, j) if j < 2 else (2, j)
+        for j, u in enumerate(st.elims):
+            rank[u] = (1, j)
+        for k in tabs:
+            f, _, _ = st.inputs[k]
+            t = f.buf
+            axes = table_axes[t]
+            ev_vars = {evidence[col] for col, _, _ in f.ev}
+            free = [u for u in axes if u not in ev_vars]
+            assert set(free) == set(f.vars) and all(u in rank for u in free)
+            new_axes = sorted(free, key=lambda u: rank[u], reverse=True) + [u for u in axes if u in ev_vars]
+            if new_axes == axes:
+                continue
+            table_arrays[t] = np.ascontiguousarray(np.transpose(table_arrays[t], [axes.index(u) for u in new_axes]))
+            table_axes[t] = new_axes
+            shape = [int(card[u]) for u in new_axes]
+            stride = {u: int(np.prod(shape[i + 1:], dtype=np.int64)) for i, u in enumerate(new_axes)}
+            col_of = {evidence[col]: col for col, _, _ in f.ev}
+            ev = tuple((col_of[u], stride[u], int(card[u])) for u in new_axes if u in ev_vars)
+            g = _Factor(False, t, f.vars, tuple(stride[u] for u in f.vars), ev, False)
+            st.inputs[k] = (g, tuple(stride.get(e, 0) for e in st.elims), tuple(stride.get(u, 0) for u in st.out_vars))
 
 
 def _merge_sum_outs(steps, enabled=True):

@@ -534,3 +534,33 @@ def test_impute_many_agrees_with_row_by_row_impute():
         want = bn.impute(row)
         for c in holes.columns:
             assert filled.loc[i, c] == want[c], (i, c)
+
+
+def test_sliced_staging_of_big_cpts_matches_the_oracle():
+    """dag50 has 8^5-entry CPTs (128 KB): the planner lays them out for their consumer and the
+    tiled kernel stages, per chunk of tiles, only the slice those tiles touch.  Against the oracle,
+    and against the plain kernel that gathers the same tables from L1/L2."""
+    from oracle import ve_oracle
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.dag50()
+    bn = wl.build()
+    net = bn._compiled
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    assert any(sum(net.cpt[plan.tables[f.buf]].size for f, _, _ in st.inputs if not f.is_slot) * 4 > planner.SLICE_MIN_BYTES
+               for st in plan.steps if st.kind == planner.KIND_BATCHED)
+    B = 2_000
+    codes = wl.codes(bn, B, seed=31)
+    prog = engine.Program(plan)
+    tiled = prog.run(codes, B).copy()
+    prog.set_tiled(False)
+    plain = prog.run(codes, B).copy()
+    assert np.allclose(tiled, plain, rtol=5e-6, atol=1e-30)
+    order = [net.names[v] for v in plan.order]
+    worst = 0.0
+    for b in range(0, B, 211):
+        ev = {v: net.domains[net.index[v]][int(codes[k, b])] for k, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        worst = max(worst, rel_err(tiled[:, b], want))
+    assert worst < RTOL, worst

@@ -330,3 +330,31 @@ def test_every_step_respects_the_kernel_limits():
             # slot sizes cover what is written into them
             for st in plan.steps:
                 assert plan.slots[st.out_slot][1] >= (int(np.prod(st.cards, dtype=np.int64)) if st.cards else 1)
+
+
+def test_big_cpts_are_laid_out_for_their_consumer():
+    """A launch whose tables exceed the shared-memory budget gets them re-shipped with the output
+    axes >= 2 outermost (sliced staging, csrc plan_slices): same answers as the oracle, and the
+    tiles of one value of the outermost axis touch one contiguous part of the table."""
+    wl = workloads.dag50()
+    bn = wl.build()
+    net = bn._compiled
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    big = [(st, f, ss) for st in plan.steps if st.kind == planner.KIND_BATCHED
+           for f, _, ss in st.inputs if not f.is_slot and net.cpt[plan.tables[f.buf]].size * 4 > planner.SLICE_MIN_BYTES]
+    assert big
+    for st, f, ss in big:
+        rest = [s for s in ss[2:] if s]
+        inner = [s for s in ss[:2] if s] + [s for _, s, _ in f.ev]
+        if rest:  # (a table of a one- or two-axis launch has nothing to slice along)
+            assert min(rest) > max(inner)  # axes >= 2 are the outermost ones
+            assert rest == sorted(rest)  # ... in the significance order the tiles are walked in
+    assert any(s for _, _, ss in big for s in ss[2:])
+    codes = wl.codes(bn, 3, seed=31)
+    got = program_interp.run(plan.words, plan.table_blob64, codes)
+    order = [net.names[v] for v in plan.order]
+    for b in range(3):
+        ev = {v: net.domains[net.index[v]][int(codes[k, b])] for k, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        assert np.allclose(got[:, b], want, rtol=1e-10, atol=0)
