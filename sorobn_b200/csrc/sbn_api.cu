@@ -319,7 +319,9 @@ constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one s
 int64_t slice_budget() {
     static const int64_t v = [] {
         const char *e = getenv("SOROBN_B200_SLICE_KB");
-        const int64_t kb = e ? atoll(e) : SBN_SMEM_BUDGET / 1024;
+        // swept on B200 (dag50, 1M rows): 64 KB -> 8.46 ms, 32 KB -> 8.14 ms (more CTAs per SM),
+        // 16 KB -> 10.8 ms (the launch with two 128 KB CPTs no longer fits and leaves the tiled kernel)
+        const int64_t kb = e ? atoll(e) : 32;
         return std::max<int64_t>(1024, std::min<int64_t>(kb * 1024, SBN_SMEM_BUDGET));
     }();
     return v;
