@@ -845,6 +845,8 @@ cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t gri
                 else if (preload && q.cx == 8 && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8>, g, b, smem, stream, q);
                 else if (preload && q.cx_inner == 4 && q.zoff != nullptr)
                     sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4, false, true>, g, b, smem, stream, q);
+                else if (preload && q.cx_inner == 8 && q.zoff != nullptr)
+                    sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8, false, true>, g, b, smem, stream, q);
                 else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0>, g, b, smem, stream, q);
                 break;
             default: return cudaErrorInvalidValue;
@@ -910,6 +912,7 @@ cudaError_t set_tiled_attr_c() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, TV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
         SBN_AM(2) SBN_AM(3) SBN_AM(4) SBN_AM(5)
 #undef SBN_AM
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, 4, kV, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
     }
 #undef SBN_A
     return e;
