@@ -685,7 +685,15 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
         }();
         // swept on B200 (grid workload): 3552 -> 4.20 ms, 7104 -> 4.10 ms, 14208 -> 4.23 ms
         // big tables: one CTA per SM, so few CTAs that each amortise their 100+ KB of staging
-        const int64_t target = st.big_tables ? 4 * 148 : (target_env > 0 ? target_env : 8 * 148 * 6);
+        int64_t target = st.big_tables ? 4 * 148 : (target_env > 0 ? target_env : 8 * 148 * 6);
+        static const int64_t small_env = [] {
+            const char *e = getenv("SOROBN_B200_SMALL_WAVE");
+            return e ? atoll(e) : 2000LL;
+        }();
+        // A launch with few tiles in total (at one tile per CTA: under ~4.5 waves) runs as ONE wave
+        // of CTAs that each walk all their tiles: staging and the first loads are paid once per CTA,
+        // not once per tile (grid: 3.305 -> 3.264 ms; the 125-entry table-only launches 22 -> 17 us).
+        if (small_env > 0 && !st.big_tables && st.n_tiles * n_rblocks <= small_env) target = 3 * 148;
         int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(st.n_tiles, target / std::max<int64_t>(1, n_rblocks)));
         int64_t tpc = (st.n_tiles + chunks - 1) / chunks;
         if (st.slice_pos >= 0) tpc = st.slice_tpc;  // the slices were cut for this chunk size
