@@ -531,8 +531,11 @@ def _relayout_big_tables(steps, table_arrays, table_axes, evidence, card):
         if st.kind != KIND_BATCHED:
             continue
         tabs = [k for k, (f, _, _) in enumerate(st.inputs) if not f.is_slot]
-        total = sum(table_arrays[st.inputs[k][0].buf].size for k in tabs) * 4
-        if total <= SLICE_MIN_BYTES:
+        total = sum(table_arrays[st.inputs[k][0].buf].size for k in tabs)
+        for f, _, _ in st.inputs:  # tables built by deferred evidence instantiation are staged too
+            if f.is_slot and not f.batched:
+                total += int(np.prod([card[u] for u in f.vars] + [c for _, _, c in f.ev], dtype=np.int64))
+        if total * 4 <= SLICE_MIN_BYTES:
             continue
         rank = {}  # variable -> significance (higher = outer)
         for j, u in enumerate(st.out_vars):
