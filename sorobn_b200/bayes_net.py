@@ -133,7 +133,13 @@ class BayesNet:
             if not observed:
                 raise ValueError("a row with every variable missing cannot be imputed")
             post = self.query_many(*pattern, events=samples.loc[rows, observed], **query_params)
-            best = post.to_numpy().argmax(axis=1)
+            values = post.to_numpy()
+            impossible = np.isnan(values).all(axis=1)
+            if impossible.any():
+                # `impute` raises here too (idxmax of the reference's empty posterior, bayes_net.py:902)
+                raise ValueError(f"{int(impossible.sum())} row(s) have evidence of probability zero "
+                                 f"(first: {post.index[impossible][0]!r}); they cannot be imputed")
+            best = values.argmax(axis=1)
             labels = post.columns  # joint states, variables sorted by name
             names = list(labels.names)
             for k, name in enumerate(names):
@@ -342,12 +348,16 @@ class BayesNet:
             # except the robust re-run of flagged rows (mode key "batched64")
             hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT or robust)))
             self._engine_cache[key] = hit
-            while len(self._engine_cache) > self.max_cached_programs:
-                _, old = self._engine_cache.popitem(last=False)
-                (old[1] if isinstance(old, tuple) else old).close()
+            self._evict()
         else:
             self._engine_cache.move_to_end(key)
         return hit
+
+    def _evict(self):
+        """Drop the least recently used device objects (programs and samplers) beyond the cap."""
+        while len(self._engine_cache) > self.max_cached_programs:
+            _, old = self._engine_cache.popitem(last=False)
+            (old[1] if isinstance(old, tuple) else old).close()
 
     def _encode_events(self, evidence_vars, columns):
         """State values -> uint8 codes [n_ev, B].  Unknown values get code 255 and the
@@ -423,7 +433,7 @@ class BayesNet:
                 raise KeyError(name)
         key = ("sampler", tuple(query), tuple(ev_vars))
         sampler = self._engine_cache.get(key)
-        q_sorted = sorted(query, key=str)
+        q_sorted = sorted(query)  # same key as the exact path (planner: sorted by name) and bayes_net.py:873
         if sampler is None:
             from . import engine
 
@@ -431,6 +441,7 @@ class BayesNet:
             sampler = engine.GibbsSampler(net, [net.index[q] for q in q_sorted], [net.index[e] for e in ev_vars],
                                           [net.index[v] for v in nonevents], device=self.device)
             self._engine_cache[key] = sampler
+            self._evict()
         codes, bad = self._encode_events(ev_vars, columns)
         if bad.any():
             raise ValueError("an event value is not a state of its variable")

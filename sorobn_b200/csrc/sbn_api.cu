@@ -139,6 +139,7 @@ struct sbn_program {
     int64_t graph_launches = 0;
 
     int64_t launches = 0;
+    int64_t setup_launches = 0;  // evidence-independent launches issued once at creation
 };
 
 namespace {
@@ -271,6 +272,14 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
         P->steps.push_back(std::move(st));
     }
     if (p != n) return fail(SBN_E_INVALID, "trailing words in program");
+    if (P->mode == 1) {
+        // evidence-independent tables are computed once per program (run_table_steps): their slots
+        // must not be recycled (planner: _assign_slots keep_unbatched)
+        std::vector<int> writes(P->slots.size(), 0);
+        for (const StepDesc &st : P->steps)
+            if (st.kind == 0 && ++writes[st.out_slot] > 1)
+                return fail(SBN_E_INVALID, "unbatched slot %d is written twice in a batched program", st.out_slot);
+    }
     if (P->steps.back().out_slot != P->post_slot) return fail(SBN_E_INVALID, "last step does not write the posterior");
     return SBN_OK;
 }
@@ -998,15 +1007,35 @@ cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64
     return cudaGetLastError();
 }
 
+// Evidence-independent steps of a batched program (products of CPTs, possibly keeping evidence
+// variables as ordinary axes) depend on the tables only: they run once, in create_common, and
+// every later run reads their outputs (19 of the 67 launches of the benchmark grid's step).
+inline bool hoisted(const sbn_program *P, const StepDesc &st) { return P->mode == 1 && st.kind == 0; }
+
+int run_table_steps(sbn_program *P) {
+    if (P->mode != 1) return SBN_OK;
+    SbnStep q;
+    for (const StepDesc &st : P->steps) {
+        if (!hoisted(P, st)) continue;
+        build_params(P, st, nullptr, 0, 1, &q);
+        SBN_CUDA(launch_step(P, st, q, P->stream));
+    }
+    SBN_CUDA(cudaStreamSynchronize(P->stream));
+    P->setup_launches = P->launches;
+    P->launches = 0;
+    return SBN_OK;
+}
+
 int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out, int64_t ld_out,
               cudaStream_t stream, cudaEvent_t *events) {
     SbnStep q;
     int k = 0;
     for (const StepDesc &st : P->steps) {
-        build_params(P, st, d_ev, ld_ev, n_rows, &q);
         if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
-        SBN_CUDA(launch_step(P, st, q, stream));
         ++k;
+        if (hoisted(P, st)) continue;  // computed once, when the program was created
+        build_params(P, st, d_ev, ld_ev, n_rows, &q);
+        SBN_CUDA(launch_step(P, st, q, stream));
     }
     if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
     SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, stream));
@@ -1035,13 +1064,14 @@ int issue_branched(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n
     SbnStep q;
     for (int s = 0; s < n_steps; ++s) {
         const StepDesc &st = P->steps[s];
+        if (hoisted(P, st)) continue;
         std::vector<int> deps;
         int home = -1;
         int64_t home_size = -1;
         for (const InDesc &in : st.in) {
             if (!in.is_slot) continue;
             const int w = last_writer[in.id];
-            if (w >= 0) {
+            if (w >= 0 && !hoisted(P, P->steps[w])) {
                 deps.push_back(w);
                 if (P->slots[in.id].size > home_size) {
                     home_size = P->slots[in.id].size;
@@ -1072,7 +1102,8 @@ int issue_branched(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n
     }
     // join: the origin stream waits for the tail of every branch that was used, then normalises
     std::vector<int> tail(sbn_program::kBranches, -1);
-    for (int s = 0; s < n_steps; ++s) tail[stream_of[s]] = s;
+    for (int s = 0; s < n_steps; ++s)
+        if (!hoisted(P, P->steps[s])) tail[stream_of[s]] = s;
     for (int k = 0; k < sbn_program::kBranches; ++k)
         if (tail[k] >= 0) SBN_CUDA(cudaStreamWaitEvent(origin, P->step_done[tail[k]], 0));
     SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, origin));
@@ -1210,6 +1241,8 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
         }
     }
 #undef SBN_CUDA_P
+    rc = run_table_steps(P);
+    if (rc != SBN_OK) return bail(rc);
     *out = P;
     return SBN_OK;
 }
@@ -1299,13 +1332,13 @@ static int run_device_impl(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, i
     int rc = check_run_args(P, d_ev, ld_ev, n_rows, d_out, ld_out);
     if (rc != SBN_OK) return rc;
     SBN_CUDA(cudaSetDevice(P->device));
-    if (P->reserved_rows == 0) {
+    if (n_rows > P->reserved_rows) {  // grows (never shrinks); capped by the free device memory
         rc = sbn_program_reserve(P, n_rows);
         if (rc != SBN_OK) return rc;
     }
     if (n_rows > P->reserved_rows)
-        return fail(SBN_E_INVALID, "n_rows %lld exceeds the reserved chunk of %lld rows", (long long)n_rows,
-                    (long long)P->reserved_rows);
+        return fail(SBN_E_NOMEM, "n_rows %lld exceeds the %lld rows of scratch that fit the device; use the host path "
+                    "(it runs in chunks) or smaller batches", (long long)n_rows, (long long)P->reserved_rows);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!P->use_graph) return issue_all(P, d_ev, ld_ev, n_rows, d_out, ld_out, stream, nullptr);
 
@@ -1347,7 +1380,10 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
     const size_t elem = f64 ? 8 : 4;
     char *out = static_cast<char *>(out_);
     SBN_CUDA(cudaSetDevice(P->device));
-    if (P->reserved_rows == 0) {
+    if (n_rows > P->reserved_rows) {
+        // the chunk capacity follows the largest batch seen so far (a program first used for one
+        // row must not answer a later million-row batch one row at a time); the reservation is
+        // capped by the free device memory, larger batches run in chunks
         rc = sbn_program_reserve(P, n_rows);
         if (rc != SBN_OK) return rc;
     }
@@ -1397,11 +1433,11 @@ int sbn_program_profile(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int6
     const int64_t n = static_cast<int64_t>(P->steps.size()) + 1;
     if (!step_ms || n_step_ms < n) return fail(SBN_E_INVALID, "step_ms needs %lld entries", (long long)n);
     SBN_CUDA(cudaSetDevice(P->device));
-    if (P->reserved_rows == 0) {
+    if (n_rows > P->reserved_rows) {
         rc = sbn_program_reserve(P, n_rows);
         if (rc != SBN_OK) return rc;
     }
-    if (n_rows > P->reserved_rows) return fail(SBN_E_INVALID, "n_rows exceeds the reserved chunk");
+    if (n_rows > P->reserved_rows) return fail(SBN_E_NOMEM, "n_rows exceeds the scratch that fits the device");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto &e : ev) SBN_CUDA(cudaEventCreate(&e));

@@ -785,13 +785,18 @@ __global__ void __launch_bounds__(256) sbn_step_flat(const __grid_constant__ Sbn
 // ---------------------------------------------------------------------- normalise
 // posterior[q, b] = post[q, b] / sum_q post[q, b]   (bayes_net.py:789-790)
 // One thread per evidence row; reads are coalesced across rows for every q.
-// Rows whose normaliser is below SBN_MIN_TOTAL (zero for impossible evidence, or so small
-// that fp32 underflow may have eaten addends) are written as NaN: the caller re-runs them in
-// float64 (BayesNet.query_many does) or treats them as impossible evidence.
-// Why 1e-30 is safe: every factor entry is <= 1, so an intermediate entry that contributes
-// more than 1e-7 of a normaliser T >= 1e-30 is itself >= 1e-37, i.e. a normal fp32 number
-// carrying full precision; what underflowed is bounded by ~1e5 operations x 1.4e-45
-// (the denormal quantum) = 1e-40 absolute, 1e-10 relative to T.
+// A row is written as NaN -- the caller re-runs it in float64 (BayesNet.query_many does) or
+// treats it as impossible evidence -- when its normaliser, or its smallest NON-ZERO
+// un-normalised entry, is below SBN_MIN_TOTAL (zero / NaN normalisers included).
+// Why 1e-30: every factor entry is <= 1, so an addend that contributes more than 1e-7 of an
+// entry E >= 1e-30 is itself >= 1e-37, a normal fp32 number carrying full precision; what
+// underflowed on the way is bounded by ~1e5 operations x 1.4e-45 (the denormal quantum)
+// = 1e-40 absolute, 1e-10 relative to E.  The bound is checked per ENTRY, not only on the
+// total: the stated tolerance is 1e-6 relative on every posterior entry, and an entry of
+// 1e-37 next to a total of 1e-28 (posterior 1e-9) would carry two or three digits.
+// What this cannot see is an entry that underflowed to exactly 0 (true value < 1.4e-45 with a
+// total >= 1e-30, i.e. a posterior below 1.4e-15): it is reported as the structural zero it is
+// indistinguishable from; `BayesNet.query` (one event) always runs in float64.
 #define SBN_MIN_TOTAL_F32 1e-30f
 
 template <typename T>
@@ -802,12 +807,16 @@ sbn_normalise(const T *__restrict__ post, int64_t ld, int post_batched, int Q, T
     if (b >= n_rows) return;
     const int64_t pitch = post_batched ? ld : 1;
     const int64_t base = post_batched ? b : 0;
-    T total = T(0);
-    for (int q = 0; q < Q; ++q) total += post[q * pitch + base];
+    T total = T(0), lo = min_total;  // lo: smallest non-zero entry, if any is below min_total
+    for (int q = 0; q < Q; ++q) {
+        const T v = post[q * pitch + base];
+        total += v;
+        if (v > T(0) && v < lo) lo = v;
+    }
     // the normaliser is P(event) for this row (bayes_net.py:790 divides by it; predict_proba,
-    // bayes_net.py:934, returns it); below min_total it is reported as NaN like the posterior
-    const bool ok = total >= min_total;  // false for NaN too
-    if (totals) totals[b] = ok ? total : static_cast<T>(__int_as_float(0x7fc00000));
+    // bayes_net.py:934, returns it); out of range it is reported as NaN like the posterior
+    const bool ok = total >= min_total && lo >= min_total;  // false for NaN too
     const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    if (totals) totals[b] = ok ? total : nan;
     for (int q = 0; q < Q; ++q) out[q * ld_out + b] = ok ? post[q * pitch + base] / total : nan;
 }

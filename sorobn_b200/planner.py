@@ -140,7 +140,6 @@ class Plan:
     evidence: tuple  # evidence var ids == evidence columns
     order: list  # elimination order (var ids)
     tables: list  # var ids whose CPTs are shipped, in table order
-    table_scale_log2: list
     slots: list  # (batched, size)
     steps: list
     post_slot: int
@@ -232,19 +231,6 @@ def _min_fill_order(scopes, hidden, card):
         remaining.remove(v)
         order.append(v)
     return order
-
-
-def table_scale_log2(table: np.ndarray) -> int:
-    """Power-of-two exponent applied to a CPT before it is shipped (always 0 today).
-
-    CPTs are shipped as plain probabilities: then every intermediate factor entry is
-    <= 1 (when a variable is eliminated its own CPT, which sums to one over it, is in
-    the product and every other entry is <= 1 by induction), so fp32 can never
-    overflow.  What can happen is underflow when the evidence is astronomically
-    unlikely (P(event) < ~1e-30); the engine detects that per row from the normaliser
-    (DESIGN.md "fp32 range").  The hook stays because a per-table power of two is exact
-    and cancels in the normalisation (bayes_net.py:790)."""
-    return 0
 
 
 def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None, max_in=MAX_IN,
@@ -508,10 +494,9 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
     steps = _merge_sum_outs(steps, merge_sum_outs)
     if mode == MODE_BATCHED:
         _relayout_big_tables(steps, table_arrays, table_axes, evidence, card)
-    slots, post_slot = _assign_slots(steps, post.buf)
+    slots, post_slot = _assign_slots(steps, post.buf, keep_unbatched=(mode == MODE_BATCHED))
 
     plan = Plan(mode=mode, query=q_sorted, evidence=evidence, order=list(order), tables=tables,
-                table_scale_log2=[table_scale_log2(net.cpt[v]) for v in tables],
                 slots=slots, steps=steps, post_slot=post_slot, Q=Q)
     plan._card = card
     _serialise(plan, table_arrays)
@@ -581,8 +566,10 @@ def _merge_sum_outs(steps, enabled=True):
             z = a.cx * st.cx
             if a.kind == st.kind and len(a.elims) + len(st.elims) <= MAX_ELIM and z <= MAX_Z:
                 new_inputs = []
-                for f, es, _ in a.inputs:
-                    pos = {u: sd for u, sd in zip(f.vars, f.strides)}
+                for f, es, ss in a.inputs:
+                    # the producer's own axis -> stride map: its output axes include the evidence
+                    # axes a lifted step keeps (those strides come from f.ev, not f.strides)
+                    pos = dict(zip(a.out_vars, ss))
                     new_inputs.append((f, es + tuple(pos.get(y, 0) for y in st.elims),
                                        tuple(pos.get(u, 0) for u in st.out_vars)))
                 a.inputs = new_inputs
@@ -597,10 +584,14 @@ def _merge_sum_outs(steps, enabled=True):
     return merged
 
 
-def _assign_slots(steps, post_id):
+def _assign_slots(steps, post_id, keep_unbatched=False):
     """Physical scratch slots by liveness: an output slot is taken before the step's inputs
     are released (a launch never writes a buffer it reads), best fit among the free slots
-    of the same kind, and every intermediate dies with its single consumer."""
+    of the same kind, and every intermediate dies with its single consumer.
+
+    keep_unbatched: the evidence-independent tables of a batched program are computed ONCE, when
+    the program is created (csrc/sbn_api.cu `run_table_steps`), and then read by every run; their
+    slots are never recycled (they are a few KB each)."""
     slots = []  # [batched, size, free]
     where = {}  # logical id -> physical slot
 
@@ -622,7 +613,7 @@ def _assign_slots(steps, post_id):
         for f, es, ss in st.inputs:
             if f.is_slot:
                 phys = where.pop(f.buf)
-                slots[phys][2] = True
+                slots[phys][2] = not (keep_unbatched and not slots[phys][0])
                 f = _Factor(True, phys, f.vars, f.strides, f.ev, f.batched)
             new_inputs.append((f, es, ss))
         st.inputs = new_inputs
@@ -634,8 +625,10 @@ def _serialise(plan: Plan, table_arrays):
     blob = []
     offsets = []
     off = 0
-    for arr, k in zip(table_arrays, plan.table_scale_log2):
-        t = np.ldexp(arr.astype(np.float64), k).reshape(-1)
+    for arr in table_arrays:
+        # plain probabilities: every intermediate entry is then <= 1 and fp32 cannot overflow
+        # (DESIGN.md "Precision and fp32 range")
+        t = arr.astype(np.float64).reshape(-1)
         pad = (-t.size) % 4  # keep every table 16-byte aligned and sized (bulk-TMA copies)
         offsets.append((off, t.size))
         blob.append(t)

@@ -25,7 +25,7 @@ def row_shard(n_rows: int, rank: int, world: int) -> slice:
 
 def gather_rows(local, n_rows: int, group=None, dst: int = 0, device=None):
     """Gather per-rank posteriors [Q, n_local] (row slices in rank order) into
-    [Q, n_rows] on `dst`; other ranks get None.  `local` is a numpy array or a torch
+    [Q, n_rows] on `dst` (a global rank, which must belong to `group`); other ranks get None.  `local` is a numpy array or a torch
     tensor; the collective runs on whatever backend `group` uses."""
     import torch
     import torch.distributed as dist
@@ -40,9 +40,11 @@ def gather_rows(local, n_rows: int, group=None, dst: int = 0, device=None):
     width = widest.stop - widest.start
     padded = torch.zeros((Q, width), dtype=t.dtype, device=t.device)
     padded[:, : t.shape[1]] = t
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    # `dst` is a GLOBAL rank (what dist.gather takes); inside a sub-group the group-local rank differs
+    is_dst = dist.get_rank() == dst
+    bufs = [torch.empty_like(padded) for _ in range(world)] if is_dst else None
     dist.gather(padded, bufs, dst=dst, group=group)
-    if rank != dst:
+    if not is_dst:
         return None
     parts = []
     for r in range(world):

@@ -348,6 +348,35 @@ def test_extremely_unlikely_evidence_is_rescued_in_float64():
     assert rel_err(single.to_numpy(), ve_oracle.query(dn, names[0], event={v: int(rows[v].iloc[0]) for v in ev_vars})[1]) < 1e-12
 
 
+def test_tiny_posterior_entry_next_to_a_representable_normaliser_is_rescued():
+    """The float32 range check is per ENTRY: P(event) ~ 1e-28 is above the 1e-30
+    threshold on the normaliser, but the un-normalised entry of the unlikely query state is
+    ~4e-40 (a float32 denormal: two or three digits).  The row must be flagged and settled in
+    float64 so that EVERY posterior entry -- also the one at ~4e-12 -- is within 1e-6 relative."""
+    from oracle import ve_oracle
+    from sorobn_b200 import BayesNet
+
+    evs = ["E1", "E2", "E3", "E4"]
+    bn = BayesNet(("Q", evs))
+    bn.P["Q"] = pd.Series({0: 1.0 - 1e-13, 1: 1e-13})
+    for e in evs:
+        bn.P[e] = pd.DataFrame({"Q": [0, 0, 1, 1], e: [0, 1, 0, 1], "p": [1 - 1e-7, 1e-7, 1 - 2.5e-7, 2.5e-7]})
+    bn.prepare()
+    rows = pd.DataFrame([[1, 1, 1, 1], [0, 0, 0, 0], [1, 1, 0, 0]], columns=evs)
+    got = bn.query_many("Q", events=rows).to_numpy()
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    for b in range(len(rows)):
+        ev = {v: int(rows[v].iloc[b]) for v in evs}
+        want = ve_oracle.query(dn, "Q", event=ev)[1].reshape(-1)
+        assert (want > 0).all() and np.isfinite(got[b]).all()
+        assert np.max(np.abs(got[b] - want) / want) < RTOL, (b, got[b], want)
+    # the raw float32 program really flags row 0 (normaliser 1e-28 >= 1e-30, entry 4e-40 < 1e-30)
+    plan, program = bn._plan(("Q",), tuple(evs), 1)
+    codes = np.ascontiguousarray(rows.to_numpy().T.astype(np.uint8))
+    raw = program.run(codes, len(rows))
+    assert np.isnan(raw[:, 0]).all() and np.isfinite(raw[:, 1]).all()
+
+
 def test_graph_branches_match_linear_replay_and_plain_launches():
     """The branched CUDA graph (independent elimination sub-trees in parallel, slot-reuse
     hazards as edges) must give bitwise the same posteriors as the linear graph and as
