@@ -2,33 +2,40 @@
 """Benchmark of the exact-inference hot path (see the contract in the task brief).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid10x10|asia_1m|dag50]
-                    [--rows R] [--impl b200|reference]
+                    [--rows R] [--impl b200|reference] [--no-extras] [--no-cpu-baseline]
 
 A *step* is one pass of the hot path over one batch of synthetic evidence rows:
 `rows` independent exact-inference queries (same query variables, same evidence
 variables, different observed states) per GPU.  Multi-GPU = one process per GPU
 (torchrun), evidence rows sharded across ranks (weak scaling: `rows` per GPU), the only
-collective is the final gather of the posteriors on rank 0 (NCCL), inside the timed step.
+collective is the final gather of the posteriors on rank 0 (NCCL), inside the timed step
+(`sorobn_b200.sharding.ShardedProgram`, the product's torchrun path).
 
 Rank 0 prints ONE JSON line:
   value      rows/s over all GPUs with evidence codes already resident in HBM
-  e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of the
-             evidence codes, every kernel, D2H of the posteriors, per step
+  e2e        the same metric with HOST (pinned) buffers: H2D of the evidence codes, every
+             kernel, (N > 1: the NCCL gather,) D2H of the posteriors, per step
   roofline   algorithmic HBM bytes of the step kernels / their device time vs measured peak
-  cpu_baseline  the CPU oracle (numpy port of the reference algorithm) on a bounded sample
+  cpu_baseline  N = 1 only: the reference's own pandas operators (oracle/_ref, kind "reference")
+             on a bounded sample of the same rows, with the numpy oracle port beside it
+  extra      the other BASELINE.json configs, bounded to a few seconds each:
+             alarm_single_query (configs[0]), asia_1m (configs[1]), dag50 (configs[3]; strong
+             scaling: 1M rows split over the N GPUs), gibbs (configs[4]; 10k chains x 10k
+             iterations per GPU)
 
-`--impl reference` times the CPU arm instead (the oracle port of the reference's
-variable elimination, one process per host core, bounded sample per step).
+`--impl reference` times the CPU arm instead: the reference's `pointwise_mul` / `sum_out`
+(oracle/_ref, copied from /root/reference by oracle/build_ref.py) driven in min-fill order, one
+process per host core, a bounded sample of the same workload per step.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
+import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -38,6 +45,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "exact-inference queries/sec"
 UNIT = "queries/s"
+ALARM_QUERY = ("Burglary", {"John calls": True, "Mary calls": True})  # BASELINE.json configs[0]
 
 
 def parse_args():
@@ -48,8 +56,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="grid10x10")
     ap.add_argument("--rows", type=int, default=0, help="evidence rows per GPU per step (0 = workload default)")
-    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows per core of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` block (the other BASELINE configs)")
     ap.add_argument("--dump", default="", help="write per-launch timings (JSON) here")
     return ap.parse_args()
 
@@ -114,70 +123,96 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-# --------------------------------------------------------------------- CPU baseline
-_CPU_STATE = {}  # per worker process: workload -> (compiled net, dense oracle net, evidence names, order)
+# ------------------------------------------------------------------------ CPU legs
+# Two CPU implementations of the same path, both driven in the device program's min-fill order
+# (the planner is imported only to obtain that order; it helps the CPU arm -- the reference's own
+# set-iteration order is OOM-killed on the grid):
+#   "reference"  oracle/_ref: the reference's own pandas operators (bayes_net.py:54-256)
+#   "port"       oracle/ve_oracle.py: the dense numpy restatement
+_CPU_STATE = {}
 
 
-def _cpu_state(workload):
-    if workload not in _CPU_STATE:
-        from oracle import ve_oracle
+def ref_available() -> bool:
+    from oracle import build_ref
+
+    return build_ref.available()
+
+
+def _cpu_state(workload, kind):
+    key = (workload, kind)
+    if key not in _CPU_STATE:
         from sorobn_b200 import planner, workloads
 
         wl = workloads.WORKLOADS[workload]()
         bn = wl.build()
         net = bn._compiled
-        dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
         plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
-        _CPU_STATE[workload] = (wl, net, dn, [net.names[v] for v in plan.order])
-    return _CPU_STATE[workload]
+        order = [net.names[v] for v in plan.order]
+        if kind == "reference":
+            from oracle import build_ref, ref_driver
+
+            ref = build_ref.import_reference()
+            impl = (ref, ref_driver.build_workload(ref, wl), ref_driver)
+        else:
+            from oracle import ve_oracle
+
+            impl = (ve_oracle, ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes), None)
+        _CPU_STATE[key] = (wl, net, order, impl)
+    return _CPU_STATE[key]
 
 
 def _cpu_worker(args):
-    """Answer rows [lo, hi) with the CPU oracle; network / plan setup is cached per process
-    (the warm-up map pays for it), so the timed map measures inference only."""
-    workload, codes, lo, hi = args
-    from oracle import ve_oracle
-
-    wl, net, dn, order = _cpu_state(workload)
-    t = time.perf_counter()
+    """Answer rows [lo, hi); network / plan setup is cached per process (the warm-up map pays
+    for it), so the timed map measures inference only."""
+    workload, kind, codes, lo, hi = args
+    wl, net, order, impl = _cpu_state(workload, kind)
     acc = 0.0
-    for b in range(lo, hi):
-        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
-        acc += float(ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)[0])
-    return time.perf_counter() - t, acc
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # pandas PerformanceWarning inside the reference
+        for b in range(lo, hi):
+            ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
+            if kind == "reference":
+                ref, ref_bn, drv = impl
+                acc += float(drv.ordered_query(ref, ref_bn, wl.query, ev, order).iloc[0])
+            else:
+                ve, dn, _ = impl
+                acc += float(ve.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)[0])
+    return acc
 
 
-def _cpu_warm(workload):
-    _cpu_state(workload)
+def _cpu_warm(args):
+    _cpu_state(*args)
     time.sleep(0.2)
     return os.getpid()
 
 
-def cpu_rate(workload: str, codes: np.ndarray, n_rows: int, n_procs: int):
-    """Queries/s of the CPU oracle (numpy restatement of bayes_net.py:739-794, same
-    min-fill order as the device program) on `n_rows` rows with `n_procs` processes."""
-    import multiprocessing as mp
+class CpuArm:
+    """A pool of single-threaded worker processes, one per usable host core."""
 
-    n_rows = min(n_rows, codes.shape[1])
-    if n_procs <= 1:
-        _cpu_state(workload)
-        t0 = time.perf_counter()
-        _cpu_worker((workload, codes, 0, n_rows))
-        return n_rows / (time.perf_counter() - t0)
-    bounds = np.linspace(0, n_rows, n_procs + 1).astype(int)
-    jobs = [(workload, codes, int(bounds[i]), int(bounds[i + 1])) for i in range(n_procs) if bounds[i + 1] > bounds[i]]
-    # one single-threaded worker per core: numpy's own thread pools would oversubscribe
-    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
-        os.environ[var] = "1"
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(len(jobs)) as pool:
+    def __init__(self, workload, kind, n_procs):
+        import multiprocessing as mp
+
+        self.workload, self.kind, self.n_procs = workload, kind, max(1, n_procs)
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+            os.environ[var] = "1"  # numpy's own thread pools would oversubscribe the cores
+        self.pool = mp.get_context("spawn").Pool(self.n_procs)
         # warm every worker (imports, network build, plan): chunksize 1 and as many tasks as
         # workers, each sleeping briefly so that no worker takes two
-        pool.map(_cpu_warm, [workload] * len(jobs), chunksize=1)
+        self.pool.map(_cpu_warm, [(workload, kind)] * self.n_procs, chunksize=1)
+
+    def rate(self, codes, n_rows):
+        """rows/s over `n_rows` rows spread evenly over the workers."""
+        n_rows = min(n_rows, codes.shape[1])
+        bounds = np.linspace(0, n_rows, self.n_procs + 1).astype(int)
+        jobs = [(self.workload, self.kind, codes, int(bounds[i]), int(bounds[i + 1]))
+                for i in range(self.n_procs) if bounds[i + 1] > bounds[i]]
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, jobs, chunksize=1)
-        dt = time.perf_counter() - t0
-    return n_rows / dt
+        self.pool.map(_cpu_worker, jobs, chunksize=1)
+        return n_rows / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def effective_cores() -> int:
@@ -206,6 +241,60 @@ def effective_cores() -> int:
     return max(1, n)
 
 
+# rows per core of one CPU sample (sized for ~1 s per step with the reference, ~1 s with the port)
+CPU_ROWS_PER_CORE = {
+    "reference": {"grid10x10": 2, "asia_1m": 40, "dag50": 2},
+    "port": {"grid10x10": 512, "asia_1m": 8192, "dag50": 256},
+}
+
+
+def cpu_baseline_block(workload, codes, cores, rows_per_core=0):
+    """The CPU numbers printed beside the GPU line: the reference (when oracle/_ref travelled) and
+    the numpy port, each on `cores` processes over a bounded sample of the same rows."""
+    out = {}
+    for kind in (["reference"] if ref_available() else []) + ["port"]:
+        rpc = rows_per_core or CPU_ROWS_PER_CORE[kind].get(workload, 2)
+        n = min(codes.shape[1], rpc * cores)
+        arm = CpuArm(workload, kind, cores)
+        try:
+            arm.rate(codes, max(cores, n // 4))  # warm-up pass
+            rate = arm.rate(codes, n)
+        finally:
+            arm.close()
+        out[kind] = {"value": rate, "rows": n}
+    kind = "reference" if "reference" in out else "port"
+    what = {"reference": "oracle/_ref: the reference's own pandas pointwise_mul / sum_out (bayes_net.py:54-256) "
+                         "driven in the device program's min-fill order",
+            "port": "oracle/ve_oracle.py: numpy port of the reference's variable elimination, same min-fill order"}
+    block = {"value": out[kind]["value"], "unit": UNIT, "cores": cores, "kind": kind,
+             "sample": f"first {out[kind]['rows']} evidence rows of the same batch, {cores} processes ({what[kind]})"}
+    if kind == "reference":
+        block["port"] = {"value": out["port"]["value"], "unit": UNIT, "cores": cores,
+                         "sample": f"first {out['port']['rows']} rows, {cores} processes ({what['port']})"}
+    return block
+
+
+def alarm_reference_latency(reps=30):
+    """configs[0]: wall time of the reference's own `query` (bayes_net.py:796-875) for the Alarm query."""
+    if not ref_available():
+        return None
+    from oracle import build_ref
+    from sorobn_b200 import examples
+
+    ref = build_ref.import_reference()
+    bn = examples.build(examples.NETWORKS["alarm"], cls=ref.BayesNet)
+    q, ev = ALARM_QUERY
+    ts = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(reps + 3):
+            t = time.perf_counter()
+            ans = bn.query(q, event=ev)
+            ts.append(time.perf_counter() - t)
+    return {"ms": 1e3 * float(np.median(ts[3:])), "reps": reps, "answer": {str(k): float(v) for k, v in ans.items()},
+            "impl": "oracle/_ref BayesNet.query(algorithm='exact'), one host core"}
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -229,6 +318,12 @@ def ncu_traffic(workload: str):
     return None
 
 
+def workload_config(wl, rows, world):
+    """The `config` both arms print (identical dicts: same workload, same rows per step per GPU)."""
+    return {"workload": wl.name, "description": wl.description, "rows_per_gpu": rows, "global_rows": rows * world,
+            "query": list(wl.query), "n_evidence": len(wl.evidence), "elimination_order": "min-fill"}
+
+
 # ------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -238,32 +333,271 @@ def run_reference(args, rank, world):
     wl = workloads.WORKLOADS[args.workload]()
     bn = wl.build()
     cores = effective_cores()
-    sample = args.cpu_rows or {"grid10x10": 512 * cores, "asia_1m": 20000 * cores, "dag50": 256 * cores}.get(args.workload, 256 * cores)
-    codes = wl.codes(bn, sample, seed=0)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_rate(args.workload, codes, max(cores, sample // 8), cores)
-    rates = [cpu_rate(args.workload, codes, sample, cores) for _ in range(max(1, args.steps))]
+    kind = "reference" if ref_available() else "port"
+    rpc = args.cpu_rows or CPU_ROWS_PER_CORE[kind].get(args.workload, 2)
+    sample = rpc * cores
+    rows = args.rows or wl.default_rows
+    codes = wl.codes(bn, max(sample, 512 * cores), seed=1000)  # the rows rank 0 of the GPU arm answers
+    arm = CpuArm(args.workload, kind, cores)
+    try:
+        for _ in range(max(0, args.warmup)):
+            arm.rate(codes, sample)
+        rates = [arm.rate(codes, sample) for _ in range(max(1, args.steps))]
+    finally:
+        arm.close()
     value = float(np.mean(rates))
+    what = ("oracle/_ref = the reference's own pandas pointwise_mul / sum_out (bayes_net.py:54-256, copied unmodified "
+            "from /root/reference by oracle/build_ref.py) driven in min-fill order; the reference's own set-order "
+            "elimination is OOM-killed on the grid" if kind == "reference" else
+            "oracle/ve_oracle.py, numpy port of the reference's variable elimination (oracle/_ref did not travel)")
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{sample} evidence rows ({rpc} per core) of the same workload per step, {cores} single-threaded "
+                     f"processes; {what}"}
+    if kind == "reference":
+        port = CpuArm(args.workload, "port", cores)
+        try:
+            n_port = CPU_ROWS_PER_CORE["port"].get(args.workload, 256) * cores
+            port.rate(codes, n_port // 4)
+            cpu["port"] = {"value": port.rate(codes, n_port), "unit": UNIT, "cores": cores,
+                           "sample": f"{n_port} rows, {cores} processes (oracle/ve_oracle.py numpy port)"}
+        finally:
+            port.close()
+    extra = {}
+    if not args.no_extras:
+        lat = alarm_reference_latency()
+        if lat:
+            extra["alarm_single_query"] = lat
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.name, "description": wl.description, "rows_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} evidence rows of the same workload per step, {cores} processes "
-                                   "(numpy oracle port of the reference's variable elimination, min-fill order)"},
+        "config": workload_config(wl, rows, world),
+        "sample_rows_per_step": sample,
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------- B200 arm
+class Timer:
+    """Device timing of `steps` calls of fn(): CUDA events on the current stream, a barrier +
+    synchronize on both sides, optional L2 flush (a 256 MB write) before every timed call."""
+
+    def __init__(self, torch, dist, distributed, dev):
+        self.torch, self.dist, self.distributed, self.dev = torch, dist, distributed, dev
+        self._flush = None
+
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_buffer(self):
+        if self._flush is None:
+            self._flush = self.torch.empty(256 * 1024 * 1024, dtype=self.torch.uint8, device=self.dev)
+        return self._flush
+
+    def device_ms(self, fn, steps, flush):
+        torch = self.torch
+        if not flush:
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.barrier()
+            start.record()
+            for _ in range(steps):
+                fn()
+            end.record()
+            self.barrier()
+            return start.elapsed_time(end)
+        total = 0.0
+        for _ in range(steps):
+            self.flush_buffer().fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.barrier()
+            s.record()
+            fn()
+            e.record()
+            self.barrier()
+            total += s.elapsed_time(e)
+        return total
+
+    def wall_s(self, fn, steps):
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        return time.perf_counter() - t0
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.distributed:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def exact_workload(ctx, wl, rows, steps, warmup, want_profile=False, counts=None):
+    """Time one exact-inference workload on this rank's GPU (+ gather when distributed).
+    Returns a dict on rank 0 (None elsewhere): device-timed and end-to-end numbers."""
+    import torch
+
+    from sorobn_b200 import engine, planner, sharding
+
+    tm, rank, world, local_rank, dev = ctx["timer"], ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dev"]
+    bn = wl.build(device=local_rank)
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    prog = engine.Program(plan, device=local_rank)
+    prog.reserve(rows)
+    reserved = prog.info()["reserved_rows"]
+    assert reserved >= rows, f"scratch for {rows} rows does not fit (got {reserved})"
+    n_ev, Q = prog.n_ev, prog.Q
+    codes_host = engine.PinnedArray((max(n_ev, 1), rows), np.uint8)
+    codes_host.array[:n_ev] = wl.codes(bn, rows, seed=1000 + rank)
+    out_host = engine.PinnedArray((Q, rows), np.float32)
+    distributed = world > 1
+    step_bytes = plan.bytes_per_row() * rows
+    flush = step_bytes < 512e6  # working set could sit in the 126 MB L2: flush between steps
+
+    if distributed:
+        sp = sharding.ShardedProgram(prog, Q, n_ev, rows, dst=0, device=dev)
+        sp.upload(codes_host.array[:n_ev])
+        d_out = sp.d_out
+        device_step = lambda: sp.run_resident(rows)  # noqa: E731
+        host_step = lambda: sp.run_host(codes_host.array[:n_ev], rows, counts=counts)  # noqa: E731
+        e2e_api = "sharding.ShardedProgram.run_host: pinned H2D, sbn_program_run_device, NCCL gather, D2H on rank 0"
+    else:
+        d_ev = torch.from_numpy(codes_host.array).to(dev)
+        d_out = torch.empty((Q, rows), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        device_step = lambda: prog.run_device(d_ev.data_ptr(), rows, rows, d_out.data_ptr(), rows, stream)  # noqa: E731
+        host_step = lambda: prog.run(codes_host.array[:n_ev], rows, out=out_host.array)  # noqa: E731
+        e2e_api = "sbn_program_run_host (pinned host buffers)"
+
+    for _ in range(warmup):
+        device_step()
+    tm.barrier()
+    launches0 = prog.info()["launches"]
+    dev_ms = tm.device_ms(device_step, steps, flush)
+    launches = prog.info()["launches"] - launches0
+    for _ in range(max(1, warmup // 2)):
+        host_step()
+    e2e_s = tm.wall_s(host_step, steps)
+    dev_ms, e2e_s = tm.max_over_ranks(dev_ms, e2e_s)
+
+    sums = d_out[:, :rows].sum(dim=0)
+    ok = bool(torch.isfinite(sums).all() and ((sums - 1).abs() < 1e-4).all())
+    if rank != 0:
+        return None
+    same = True
+    if not distributed:
+        same = bool(np.array_equal(out_host.array, d_out.cpu().numpy()))
+    ms_per_step = dev_ms / steps
+    total_rows = rows * world if counts is None else int(sum(counts))
+    res = {
+        "plan": plan, "prog": prog, "bn": bn, "codes_host": codes_host, "rows": rows, "flush": flush,
+        "ms_per_step": ms_per_step, "value": total_rows / (ms_per_step * 1e-3),
+        "e2e_ms_per_step": 1e3 * e2e_s / steps, "e2e_value": total_rows / (e2e_s / steps),
+        "h2d": int(n_ev * rows) * world, "d2h": int(Q * rows * 4) * world, "e2e_api": e2e_api,
+        "launches": int(launches) * world, "ok": ok, "same": same, "total_rows": total_rows,
+        "whole_step_frac": (plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9) / measured_peak()[0],
+    }
+    if want_profile and not distributed:
+        d_ev_ptr = d_ev.data_ptr()
+        prof = None
+        for _ in range(3):
+            t = prog.profile(d_ev_ptr, rows, rows, d_out.data_ptr(), rows, stream)
+            prof = t if prof is None else np.minimum(prof, t)
+        res["profile_ms"] = prof
+    return res
+
+
+def summarise_exact(res, wl):
+    """JSON block of one `extra` exact workload."""
+    plan = res["plan"]
+    return {
+        "workload": wl.name, "rows_per_gpu": res["rows"], "global_rows": res["total_rows"],
+        "value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"],
+        "e2e": {"value": res["e2e_value"], "unit": UNIT, "ms_per_step": res["e2e_ms_per_step"],
+                "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"], "api": res["e2e_api"]},
+        "algorithmic_bytes_per_row": plan.bytes_per_row(), "hbm_roofline_frac_whole_step": res["whole_step_frac"],
+        "launches_per_step": res["launches"] // max(1, res.get("steps", 1)),
+        "l2": "flushed (256 MB write) between timed steps" if res["flush"] else "not flushed (step streams >> 126 MB)",
+        "checks": {"posteriors_sum_to_one": res["ok"], "host_path_equals_device_path": res["same"]},
+    }
+
+
+def gibbs_extra(ctx, steps, warmup):
+    """configs[4]: Gibbs sampling on the 100-node grid, 10k chains x 10k iterations per GPU (the
+    chain frequencies are gathered on rank 0 with NCCL when N > 1)."""
+    import torch
+    import torch.distributed as dist
+
+    from sorobn_b200 import engine, workloads
+
+    tm, rank, world, local_rank, dev = ctx["timer"], ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dev"]
+    wl = workloads.grid10x10()
+    bn = wl.build(device=local_rank)
+    net = bn._compiled
+    n_chains, n_iter = 10_000, 10_000
+    q_ids = [net.index[q] for q in wl.query]
+    ev_ids = [net.index[e] for e in wl.evidence]
+    cycle = [net.index[v] for v in sorted(set(bn.nodes) - set(wl.evidence))]
+    sampler = engine.GibbsSampler(net, q_ids, ev_ids, cycle, device=local_rank)
+    codes = wl.codes(bn, 1, seed=77)
+    codes = np.ascontiguousarray(np.repeat(codes, n_chains, axis=1))  # every chain: the same event
+    gathered = torch.empty((world, sampler.Q, n_chains), dtype=torch.float32, device=dev) if rank == 0 else None
+
+    def step():
+        freq = sampler.run(codes, n_chains, n_iter, seed=1234 + rank)
+        if world > 1:
+            t = torch.from_numpy(freq).to(dev)
+            dist.gather(t, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+        return freq
+
+    for _ in range(max(1, warmup // 2)):
+        freq = step()
+    s = tm.wall_s(step, steps)
+    (s,) = tm.max_over_ranks(s)
+    if rank != 0:
+        return None
+    # sanity: the mean over chains approaches the exact posterior of that event
+    exact = bn.query_many(*wl.query, events=wl.events(1, seed=77, bn=bn)).to_numpy()[0]
+    est = freq.mean(axis=1)
+    updates = n_chains * n_iter * world
+    return {"chains_per_gpu": n_chains, "iterations": n_iter, "n_cycle": len(cycle), "ms_per_run": 1e3 * s / steps,
+            "value": updates / (s / steps), "unit": "variable updates/s (whole job, host in/out included)",
+            "max_abs_error_of_chain_mean_vs_exact": float(np.max(np.abs(est - exact))),
+            "api": "sbn_sampler_run_host (one chain per evidence row)" + ("; NCCL gather of frequencies" if world > 1 else "")}
+
+
+def alarm_extra(local_rank):
+    """configs[0] on the GPU side: `BayesNet.query` for the Alarm query, cold (first call: planning,
+    program creation, table launches, run) and warm (median of 200 calls)."""
+    from sorobn_b200 import examples
+
+    q, ev = ALARM_QUERY
+    bn = examples.build(examples.NETWORKS["alarm"], device=local_rank)
+    t = time.perf_counter()
+    ans = bn.query(q, event=ev)
+    cold = time.perf_counter() - t
+    ts = []
+    for _ in range(200):
+        t = time.perf_counter()
+        bn.query(q, event=ev)
+        ts.append(time.perf_counter() - t)
+    return {"cold_ms": 1e3 * cold, "warm_ms": 1e3 * float(np.median(ts)), "reps": 200,
+            "answer": {str(k): float(v) for k, v in ans.items()},
+            "impl": "sorobn_b200.BayesNet.query (float64 single-event program, sbn_program_run_host_f64)"}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from sorobn_b200 import engine, planner, workloads
+    from sorobn_b200 import planner, sharding, workloads
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -283,154 +617,110 @@ def run_b200(args, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
 
+    ctx = {"timer": Timer(torch, dist, distributed, dev), "rank": rank, "world": world, "local_rank": local_rank,
+           "dev": dev}
     wl = workloads.WORKLOADS[args.workload]()
-    bn = wl.build(device=local_rank)
-    net = bn._compiled
-    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
-    prog = engine.Program(plan, device=local_rank)
     rows = args.rows or wl.default_rows
-    prog.reserve(rows)
-    reserved = prog.info()["reserved_rows"]
-    assert reserved >= rows, f"scratch for {rows} rows does not fit (got {reserved})"
-
-    n_ev, Q = prog.n_ev, prog.Q
-    codes_host = engine.PinnedArray((max(n_ev, 1), rows), np.uint8)
-    codes_host.array[:n_ev] = wl.codes(bn, rows, seed=1000 + rank)
-    out_host = engine.PinnedArray((Q, rows), np.float32)
-    d_ev = torch.from_numpy(codes_host.array).to(dev)
-    d_out = torch.empty((Q, rows), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world, Q, rows), dtype=torch.float32, device=dev) if distributed and rank == 0 else None
-    stream = torch.cuda.current_stream().cuda_stream
-
-    step_bytes = plan.bytes_per_row() * rows
-    flush = None
-    if step_bytes < 512e6:  # working set could sit in the 126 MB L2: flush between steps
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def device_step():
-        prog.run_device(d_ev.data_ptr(), rows, rows, d_out.data_ptr(), rows, stream)
-        if distributed:
-            dist.gather(d_out, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank)
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    launches0 = prog.info()["launches"]
-
     clocks.begin()
-    if True:
-        if flush is None:
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            start.record()
-            for _ in range(args.steps):
-                device_step()
-            end.record()
-            barrier()
-            dev_ms = start.elapsed_time(end)
-        else:
-            dev_ms = 0.0
-            for _ in range(args.steps):
-                flush.fill_(1)
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                barrier()
-                s.record()
-                device_step()
-                e.record()
-                barrier()
-                dev_ms += s.elapsed_time(e)
-        launches = prog.info()["launches"] - launches0
-
-        # ---- end to end through the C ABI with host buffers ----------------------------
-        for _ in range(max(1, args.warmup // 2)):
-            prog.run(codes_host.array[:n_ev], rows, out=out_host.array)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            prog.run(codes_host.array[:n_ev], rows, out=out_host.array)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+    res = exact_workload(ctx, wl, rows, args.steps, args.warmup, want_profile=True)
     clocks.end()
     clock_summary = clocks.summary()
     clocks.close()
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
-
-    # correctness guard of the timed outputs: every posterior sums to one
-    sums = d_out.sum(dim=0)
-    ok = bool(torch.isfinite(sums).all() and ((sums - 1).abs() < 1e-4).all())
-    same = np.allclose(out_host.array, d_out.cpu().numpy(), rtol=0, atol=0)
+    # ---- the other BASELINE configs, a few seconds each (every rank takes part in the collectives)
+    extra = {}
+    if not args.no_extras:
+        k, w = max(3, min(args.steps, 5)), 3
+        for name in ("asia_1m", "dag50"):
+            if name == wl.name:
+                continue
+            wl2 = workloads.WORKLOADS[name]()
+            counts = None
+            rows2 = wl2.default_rows
+            if name == "dag50" and world > 1:  # configs[3]: 1M queries sharded over the GPUs (strong scaling)
+                counts = [s.stop - s.start for s in (sharding.row_shard(wl2.default_rows, r, world) for r in range(world))]
+                rows2 = counts[rank]
+            r2 = exact_workload(ctx, wl2, rows2, k, w, counts=counts)
+            if rank == 0:
+                r2["steps"] = k
+                extra[name] = summarise_exact(r2, wl2)
+                extra[name]["scaling"] = "strong (1M rows over all GPUs)" if counts else "single GPU"
+        g = gibbs_extra(ctx, 3, 2)
+        if rank == 0:
+            extra["gibbs"] = g
+            extra["alarm_single_query"] = {"b200": alarm_extra(local_rank)}
 
     if rank == 0:
-        ms_per_step = dev_ms / args.steps
-        total_rows = rows * world
-        value = total_rows / (ms_per_step * 1e-3)
-        e2e_value = total_rows / (e2e_s / args.steps)
-
-        # per-launch timings of one step (CUDA events around every launch, same stream)
-        prof = prog.profile(d_ev.data_ptr(), rows, rows, d_out.data_ptr(), rows, stream)
-        sb = plan.step_bytes_per_row()
-        kernel_ms = float(sum(ms for ms, st in zip(prof[:-1], plan.steps) if st.kind == planner.KIND_BATCHED))
-        kernel_bytes = float(sum(sb)) * rows
+        plan, prog = res["plan"], res["prog"]
+        net = res["bn"]._compiled
+        ms_per_step = res["ms_per_step"]
         peak, peak_src = measured_peak()
-        achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-        roofline = {
-            "bound": "hbm", "kernel": "sbn_step_tiled (+ sbn_step_batched on sum-out-only steps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src,
-            "algorithmic_bytes_per_step": kernel_bytes, "kernel_ms_per_step": kernel_ms,
-            "launches_per_step": int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED)),
-            "whole_step_frac": (plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9) / peak,
-            "traffic": (ncu_traffic(wl.name) or {}).get("dram_bytes_per_step") if rows == wl.default_rows else None,
-            "traffic_detail": ncu_traffic(wl.name) if rows == wl.default_rows else None,
-        }
-        if args.dump:
-            with open(args.dump, "w") as f:
-                json.dump({"workload": wl.name, "rows": rows, "step_ms": [float(x) for x in prof],
-                           "step_bytes_per_row": sb,
-                           "steps": [{"kind": st.kind, "cx": st.cx, "cards": list(st.cards),
-                                      "inputs": [("B" if fct.batched else "t") + str(int(np.prod([net.card[v] for v in fct.vars])) if fct.vars else 1)
-                                                 + (f"e{len(fct.ev)}" if fct.ev else "") for fct, _, _ in st.inputs]}
-                                     for st in plan.steps]}, f)
+        roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                    "whole_step_frac": res["whole_step_frac"]}
+        if "profile_ms" in res:
+            # per-launch CUDA events (same stream, outside the graph: a few us of overhead each), used
+            # only for the SHARE of the step the step kernels take; the time itself is the timed region's
+            prof = res["profile_ms"]
+            sb = plan.step_bytes_per_row()
+            kern = float(sum(ms for ms, st in zip(prof[:-1], plan.steps) if st.kind == planner.KIND_BATCHED))
+            share = kern / float(prof.sum()) if prof.sum() > 0 else 1.0
+            kernel_ms = ms_per_step * share
+            kernel_bytes = float(sum(sb)) * rows
+            achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
+            traffic = ncu_traffic(wl.name) if rows == wl.default_rows else None
+            roofline.update({
+                "kernel": "sbn_step_tiled (every batched step of the program)", "achieved": achieved, "frac": achieved / peak,
+                "algorithmic_bytes_per_step": kernel_bytes, "kernel_ms_per_step": kernel_ms,
+                "kernel_share_of_step": share,
+                "launches_per_step": int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED)),
+                "traffic": (traffic or {}).get("dram_bytes_per_step"), "traffic_detail": traffic,
+            })
+            if args.dump:
+                with open(args.dump, "w") as f:
+                    json.dump({"workload": wl.name, "rows": rows, "step_ms": [float(x) for x in prof],
+                               "step_bytes_per_row": sb,
+                               "steps": [{"kind": st.kind, "cx": st.cx, "cards": list(st.cards),
+                                          "inputs": [("B" if fct.batched else "t") + str(int(np.prod([net.card[v] for v in fct.vars])) if fct.vars else 1)
+                                                     + (f"e{len(fct.ev)}" if fct.ev else "") for fct, _, _ in st.inputs]}
+                                         for st in plan.steps]}, f)
+        else:
+            achieved = plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9
+            roofline.update({"kernel": "whole step (per-launch profile only at N = 1)", "achieved": achieved,
+                             "frac": achieved / peak, "traffic": None})
 
         cpu = None
-        if not args.no_cpu_baseline:
-            n_cpu = args.cpu_rows or {"grid10x10": 8192, "asia_1m": 100000, "dag50": 4096}.get(wl.name, 4096)
-            codes_cpu = np.ascontiguousarray(codes_host.array[:n_ev, :n_cpu])
-            rate = cpu_rate(wl.name, codes_cpu, n_cpu, 1)
-            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"first {n_cpu} evidence rows of the same batch, single process "
-                             "(oracle/ve_oracle.py: numpy port of the reference's variable elimination, "
-                             "same min-fill order)"}
+        if not args.no_cpu_baseline and not distributed:
+            cores = effective_cores()
+            cpu = cpu_baseline_block(wl.name, np.ascontiguousarray(res["codes_host"].array[:prog.n_ev, :min(rows, 512 * cores)]),
+                                     cores, args.cpu_rows)
+            if not args.no_extras:
+                lat = alarm_reference_latency()
+                if lat:
+                    extra.setdefault("alarm_single_query", {})["reference_cpu"] = lat
 
+        cfg = workload_config(wl, rows, world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": wl.name, "description": wl.description, "rows_per_gpu": rows,
-                "global_rows": total_rows, "parallelism": f"rows sharded x{world}; NCCL gather of posteriors",
+            "config": cfg,
+            "plan": {
+                "parallelism": f"rows sharded x{world}; NCCL gather of posteriors",
                 "elimination_steps": len(plan.steps), "max_factor_entries_per_row": plan.max_factor_per_row(),
                 "algorithmic_bytes_per_row": plan.bytes_per_row(),
-                "l2": ("flushed (256 MB write) between timed steps" if flush is not None else
-                       f"not flushed: each step streams {step_bytes / 1e9:.2f} GB of factors >> 126 MB L2"),
+                "l2": ("flushed (256 MB write) between timed steps" if res["flush"] else
+                       f"not flushed: each step streams {plan.bytes_per_row() * rows / 1e9:.2f} GB of factors >> 126 MB L2"),
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_ev * rows) * world,
-                    "d2h_bytes_per_step": int(Q * rows * 4) * world, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "sbn_program_run_host (pinned host buffers)"},
-            "gpu_launches": int(launches) * world,
+            "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
+                    "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["e2e_ms_per_step"], "api": res["e2e_api"]},
+            "gpu_launches": res["launches"],
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clock_summary,
-            "checks": {"posteriors_sum_to_one": ok, "host_path_equals_device_path": bool(same)},
+            "checks": {"posteriors_sum_to_one": res["ok"], "host_path_equals_device_path": res["same"]},
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
 

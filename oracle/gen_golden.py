@@ -28,18 +28,13 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def import_reference():
-    stub = types.ModuleType("vose")
+    """The reference package, through the same copy (`oracle/_ref`, made by oracle/build_ref.py
+    from /root/reference) that the CPU legs of bench.py time."""
+    sys.path.insert(0, ROOT)
+    from oracle import build_ref
 
-    class Sampler:  # pragma: no cover - sampling is outside the golden cases
-        def __init__(self, weights, seed=None):
-            raise RuntimeError("vose stub: sampling is not part of the exact-inference goldens")
-
-    stub.Sampler = Sampler
-    sys.modules.setdefault("vose", stub)
-    sys.path.insert(0, REF)
-    import sorobn  # noqa: E402
-
-    return sorobn
+    assert build_ref.build() is not None, "/root/reference is needed to generate the goldens"
+    return build_ref.import_reference()
 
 
 def jsonable(v):
@@ -65,34 +60,10 @@ def run_case(bn, query, event):
 
 
 def run_case_ordered(ref, bn, query, event, order):
-    """The reference's exact inference with a GIVEN elimination order.
+    """The reference's operators driven in a given elimination order (oracle/ref_driver.py)."""
+    from oracle import ref_driver
 
-    `BayesNet._variable_elimination` (bayes_net.py:739-794) eliminates the hidden
-    nodes in Python-set iteration order, which on the 10x10 grid builds factors that
-    do not fit in memory (the process is OOM-killed).  BASELINE.json asks for the
-    min-fill order, so this drives the reference's OWN operators -- `pointwise_mul`
-    (bayes_net.py:253) and `.cdt.sum_out` (bayes_net.py:54) -- through the same loop
-    with the order fixed.  Everything numeric is still executed by the reference."""
-    pm = ref.bayes_net.pointwise_mul
-    relevant = {*query, *event}
-    for node in list(relevant):
-        relevant |= bn.ancestors(node)
-    hidden = relevant - {*query, *event}
-    assert set(order) == hidden
-    factors = []
-    for node in relevant:
-        factor = bn.P[node].copy()
-        for var, val in event.items():
-            if var in factor.index.names:
-                factor = factor[factor.index.get_level_values(var) == val]
-        factors.append(factor)
-    for node in order:
-        prod = pm(factors.pop(i) for i in reversed(range(len(factors))) if node in factors[i].index.names)
-        factors.append(prod.cdt.sum_out(node))
-    posterior = pm(factors)
-    posterior = posterior / posterior.sum()
-    posterior.index = posterior.index.droplevel(list(set(posterior.index.names) - set(query)))
-    ans = posterior.rename(f"P({', '.join(query)})").sort_index()
+    ans = ref_driver.ordered_query(ref, bn, query, event, order)
     idx = [list(map(jsonable, k)) if isinstance(k, tuple) else [jsonable(k)] for k in ans.index.tolist()]
     return {
         "query": list(query),
@@ -101,6 +72,45 @@ def run_case_ordered(ref, bn, query, event, order):
         "index": idx,
         "values": [float(x) for x in ans.to_numpy()],
     }
+
+
+def impute_cases(ref_bn, our_spec, n_cases, seed):
+    """`BayesNet.impute` (bayes_net.py:877-908) on random partial samples: 2-3 missing variables,
+    the others observed at states drawn from the network itself (positive probability).
+    With ONE missing variable the reference fails: `posterior.idxmax()` is then a scalar and
+    `zip(names, scalar)` raises TypeError (bool / int states) or walks the characters of a string
+    state (bayes_net.py:905); sorobn_b200 fills the single value, so there is nothing to pin."""
+    rng = np.random.default_rng(seed)
+    nodes = list(our_spec)
+    cases = []
+    for _ in range(n_cases):
+        full = ref_bn.sample()
+        k = int(rng.integers(2, min(3, len(nodes) - 1) + 1))
+        missing = set(rng.choice(nodes, size=k, replace=False).tolist())
+        sample = {n: (None if n in missing else jsonable(full[n])) for n in nodes}
+        filled = ref_bn.impute(dict(sample))
+        cases.append({"sample": [[n, sample[n]] for n in nodes],
+                      "filled": [[n, jsonable(filled[n])] for n in nodes]})
+    return cases
+
+
+def gibbs_conditionals(ref, ref_bn):
+    """The per-variable conditionals P(var | Markov boundary) that `_gibbs_sampling` precomputes
+    (bayes_net.py:699-712, restated line by line with the reference's own `pointwise_mul`): they
+    are deterministic, unlike the chain itself, so they pin the device sampler's on-the-fly
+    conditional exactly."""
+    pm = ref.bayes_net.pointwise_mul
+    out = {}
+    for node in sorted(ref_bn.nodes):
+        post = pm(ref_bn.P[n] for n in [node, *ref_bn.children.get(node, [])])
+        boundary = ref_bn.markov_boundary(node)
+        if boundary:
+            post = post.groupby(boundary, group_keys=False).apply(lambda g: g / g.sum())
+            post = post.reorder_levels([*boundary, node])
+        post = post.sort_index()
+        rows = [(list(map(jsonable, k)) if isinstance(k, tuple) else [jsonable(k)]) for k in post.index.tolist()]
+        out[node] = {"boundary": list(boundary), "index": rows, "values": [float(x) for x in post.to_numpy()]}
+    return out
 
 
 def example_cases(ref_bn, our_spec):
@@ -196,6 +206,17 @@ def main():
         with open(os.path.join(OUT, f"predict_proba_{name}.json"), "w") as f:
             json.dump({"network": name, "kind": "predict_proba", "cases": cases}, f)
         print(f"predict_proba {name}: {len(cases)} cases, {sum(len(c['rows']) for c in cases)} rows")
+
+    # ---- impute (bayes_net.py:877-908) and the Gibbs conditionals (bayes_net.py:699-712) ------
+    for name, spec in ({} if only_workload else examples.NETWORKS).items():
+        ref_bn = examples.build(spec, cls=ref.BayesNet, seed=7)
+        cases = impute_cases(ref_bn, spec, 25, seed=3)
+        with open(os.path.join(OUT, f"impute_{name}.json"), "w") as f:
+            json.dump({"network": name, "kind": "impute", "cases": cases}, f)
+        cond = gibbs_conditionals(ref, ref_bn)
+        with open(os.path.join(OUT, f"gibbs_conditionals_{name}.json"), "w") as f:
+            json.dump({"network": name, "kind": "gibbs_conditionals", "nodes": cond}, f)
+        print(f"impute {name}: {len(cases)} cases; gibbs conditionals: {sum(len(c['values']) for c in cond.values())} entries")
 
     # ---- synthetic networks ----------------------------------------------------------
     jobs = [

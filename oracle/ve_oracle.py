@@ -312,3 +312,35 @@ def brute_force_query(net: DenseNet, query_vars, event: dict):
     vals = vals.sum(axis=drop)
     return tuple(v for v in keep if v in query_vars), vals / vals.sum()
 
+
+
+def impute(net: DenseNet, sample: dict) -> dict:
+    """`BayesNet.impute` (bayes_net.py:877-908): the `None` entries of `sample` are replaced by
+    the most probable joint state of the missing variables given the others (`idxmax` of the
+    exact posterior: the first maximum in sorted-index order)."""
+    missing = [k for k, v in sample.items() if v is None]
+    event = {k: v for k, v in sample.items() if v is not None}
+    names, values, _ = query(net, *missing, event=event)
+    best = np.unravel_index(int(np.argmax(values)), values.shape)  # C order == sorted MultiIndex order
+    filled = dict(event)
+    for name, idx in zip(names, best):
+        filled[name] = net.domains[name][idx]
+    return filled
+
+
+def gibbs_conditional(net: DenseNet, node):
+    """P(node | Markov boundary), the table `_gibbs_sampling` precomputes for every non-event
+    variable (bayes_net.py:699-712): the product of the node's CPT and its children's CPTs,
+    normalised over the node for every configuration of the boundary.
+
+    Returns (boundary, table): boundary = parents, children and the children's other parents,
+    sorted (bayes_net.py:1002-1039); table has axes [*boundary, node].  Configurations whose
+    product is zero for every state (which the reference's zero-dropping join leaves out) are NaN."""
+    children = [c for c in net.nodes if node in net.parents.get(c, ())]
+    prod = pointwise_mul([Factor(net.scope(n), net.cpt[n]) for n in [node, *children]])
+    boundary = sorted(v for v in prod.vars if v != node)
+    perm = [prod.vars.index(v) for v in [*boundary, node]]
+    vals = np.transpose(prod.values, perm)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        table = vals / vals.sum(axis=-1, keepdims=True)
+    return boundary, table

@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import graphlib
 import random
+import threading
 import typing
 from collections import OrderedDict, defaultdict
 
@@ -83,7 +84,20 @@ class BayesNet:
         # compiled device programs, one per (query vars, evidence vars, mode); least recently
         # used ones are dropped (their streams, graph and scratch are freed with them)
         self._engine_cache = OrderedDict()
+        self._cache_lock = threading.RLock()  # query_many(devices=...) looks programs up from worker threads
         self.max_cached_programs = 128
+
+    def __getstate__(self):
+        """Copies and pickles carry the network, not the device objects (programs hold CUDA
+        handles that must have exactly one owner); they are rebuilt on first use."""
+        state = self.__dict__.copy()
+        state["_engine_cache"] = OrderedDict()
+        state.pop("_cache_lock", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._cache_lock = threading.RLock()
 
     # ------------------------------------------------------------------ structure
     def ancestors(self, node):
@@ -328,25 +342,32 @@ class BayesNet:
         return frame if n > 1 else frame.iloc[0]
 
     # ---------------------------------------------------------------------- query
-    def _plan(self, query, evidence_vars, mode, robust=False):
+    def _plan(self, query, evidence_vars, mode, robust=False, device=None):
+        with self._cache_lock:
+            return self._plan_locked(query, evidence_vars, mode, robust, device)
+
+    def _plan_locked(self, query, evidence_vars, mode, robust, device):
         if self._compiled is None:
             self._compile()
             if self._compiled is None:
                 raise ValueError("every node needs a CPT in P before querying; call prepare()")
         net = self._compiled
-        key = (tuple(query), tuple(evidence_vars), mode, robust)
+        device = self.device if device is None else device
+        key = (tuple(query), tuple(evidence_vars), mode, robust, device)
         hit = self._engine_cache.get(key)
         if hit is None:
             for name in (*query, *evidence_vars):
                 if name not in net.index:
                     raise KeyError(name)
-            plan = _planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evidence_vars],
-                                       mode=mode, allow_empty_query=True)
+            twin = next((v for k, v in self._engine_cache.items() if isinstance(v, tuple) and k[:4] == key[:4]), None)
+            plan = twin[0] if twin else _planner.build_plan(
+                net, [net.index[q] for q in query], [net.index[e] for e in evidence_vars],
+                mode=mode, allow_empty_query=True)  # the same plan serves every device
             from . import engine  # raises if libsorobn_b200.so cannot be loaded
 
             # single-event programs run in float64 (latency-bound anyway); batches in float32,
             # except the robust re-run of flagged rows (mode key "batched64")
-            hit = (plan, engine.Program(plan, device=self.device, f64=(mode == _planner.MODE_FLAT or robust)))
+            hit = (plan, engine.Program(plan, device=device, f64=(mode == _planner.MODE_FLAT or robust)))
             self._engine_cache[key] = hit
             self._evict()
         else:
@@ -450,11 +471,17 @@ class BayesNet:
         index = pd.Index(doms[0], name=q_sorted[0]) if len(q_sorted) == 1 else pd.MultiIndex.from_product(doms, names=q_sorted)
         return freq, index
 
-    def query_many(self, *query, events: pd.DataFrame, algorithm="exact", n_iterations=100) -> pd.DataFrame:
+    def query_many(self, *query, events: pd.DataFrame, algorithm="exact", n_iterations=100,
+                   devices: typing.Sequence[int] | None = None) -> pd.DataFrame:
         """Batched `query`: one posterior per row of `events` (columns = evidence
         variables).  Returns a DataFrame with one row per evidence row and one column
         per joint state of the query variables (same order as `query`'s index);
-        impossible rows are NaN.  Zero-probability states stay (as 0.0)."""
+        impossible rows are NaN.  Zero-probability states stay (as 0.0).
+
+        devices: CUDA device ids to shard the rows over (exact algorithm).  Rows are independent,
+        so each device answers a contiguous slice with its own program (one host thread per
+        device; the C ABI call releases the GIL) and the slices land in one host array: there is
+        no collective.  One process per GPU under torchrun is `sorobn_b200.sharding.query_many_sharded`."""
         if not query:
             raise ValueError("At least one query variable has to be specified")
         ev_vars = tuple(events.columns)
@@ -467,29 +494,75 @@ class BayesNet:
             return pd.DataFrame(freq.T.astype(np.float64), index=events.index, columns=index)
         if algorithm != "exact":
             raise ValueError("Unknown algorithm, must be one of: exact, gibbs, likelihood, rejection")
-        plan, program = self._plan(query, ev_vars, _planner.MODE_BATCHED)
+        plan, _ = self._plan(query, ev_vars, _planner.MODE_BATCHED, device=None if devices is None else devices[0])
         n = len(events.index)
         if n == 0:
             return pd.DataFrame(np.zeros((0, plan.Q)), index=events.index, columns=self._answer_index(plan))
         codes, bad = self._encode_events(ev_vars, [events[v].to_numpy() for v in ev_vars])
         if not ev_vars:
             bad = np.zeros(n, dtype=bool)
-        post = program.run(codes, n).astype(np.float64)  # [Q, n]
-        # NaN rows: impossible evidence, or a normaliser so small that float32 may have
-        # underflowed -- settle those one by one with the float64 single-event program
-        suspect = np.isnan(post).any(axis=0) & ~bad
-        rows = np.nonzero(suspect)[0]
-        if len(rows) > 8:  # many rows below the float32 range: one batched float64 run
-            _, robust = self._plan(query, ev_vars, _planner.MODE_BATCHED, robust=True)
-            post[:, rows] = robust.run(np.ascontiguousarray(codes[:, rows]), len(rows))
-        elif len(rows):
-            _, flat = self._plan(query, ev_vars, _planner.MODE_FLAT)
-            for b in rows:
-                post[:, b] = flat.run(np.ascontiguousarray(codes[:, b:b + 1]), 1)[:, 0]
+        if devices is None or len(devices) <= 1:
+            post = self._posterior_codes(query, ev_vars, codes, bad, device=None if devices is None else devices[0])
+        else:
+            post = self._posterior_codes_multi(query, ev_vars, codes, bad, list(devices))
         out = pd.DataFrame(post.T, index=events.index, columns=self._answer_index(plan))
         if bad.any():
             out.loc[events.index[bad]] = np.nan
         return out
+
+    def _posterior_codes(self, query, ev_vars, codes, bad, device=None):
+        """Posterior float64 [Q, n] for uint8 evidence codes [n_ev, n] on one device.  Rows the
+        float32 program flags (NaN: impossible evidence, or an entry below the float32 range)
+        are settled in float64 -- a few one by one with the single-event program, many as one
+        batch with the batched float64 program; a row that is still NaN there is impossible."""
+        n = codes.shape[1] if len(ev_vars) else len(bad)
+        _, program = self._plan(query, ev_vars, _planner.MODE_BATCHED, device=device)
+        post = program.run(codes, n).astype(np.float64)  # [Q, n]
+        suspect = np.isnan(post).any(axis=0) & ~bad
+        rows = np.nonzero(suspect)[0]
+        if len(rows) > 8:
+            _, robust = self._plan(query, ev_vars, _planner.MODE_BATCHED, robust=True, device=device)
+            post[:, rows] = robust.run(np.ascontiguousarray(codes[:, rows]), len(rows))
+        elif len(rows):
+            _, flat = self._plan(query, ev_vars, _planner.MODE_FLAT, device=device)
+            for b in rows:
+                post[:, b] = flat.run(np.ascontiguousarray(codes[:, b:b + 1]), 1)[:, 0]
+        return post
+
+    def _posterior_codes_multi(self, query, ev_vars, codes, bad, devices):
+        """Row-shard `_posterior_codes` over several GPUs of this process: contiguous balanced
+        slices (sharding.row_shard), one thread per device."""
+        import threading
+
+        from .sharding import row_shard
+
+        n = len(bad)
+        world = len(devices)
+        # programs are created up front, on this thread (the cache is not thread-safe)
+        for d in devices:
+            self._plan(query, ev_vars, _planner.MODE_BATCHED, device=d)
+        plan, _ = self._plan(query, ev_vars, _planner.MODE_BATCHED, device=devices[0])
+        post = np.empty((plan.Q, n), dtype=np.float64)
+        errors = []
+
+        def work(r):
+            sl = row_shard(n, r, world)
+            if sl.stop == sl.start:
+                return
+            try:
+                post[:, sl] = self._posterior_codes(query, ev_vars, np.ascontiguousarray(codes[:, sl]), bad[sl],
+                                                    device=devices[r])
+            except Exception as exc:  # surfaced on the calling thread
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return post
 
     # ------------------------------------------------------- joint / likelihood of rows
     def full_joint_dist(self, event: dict = None, keep_zeros=False) -> pd.Series:

@@ -121,3 +121,76 @@ def test_evidence_probability_matches_reference_predict_proba(name):
             assert abs(got - want) <= 1e-12 * max(want, 1e-300), (ev, got, want)
             idx = tuple(net.domains[v].index(ev[v]) if v in ev else slice(None) for v in joint.vars)
             assert abs(joint.values[idx].sum() - want) <= 1e-12
+
+
+def _example(name):
+    from sorobn_b200 import examples
+
+    return examples.build(examples.NETWORKS[name])
+
+
+@pytest.mark.parametrize("name", golden_names(("impute",)))
+def test_oracle_impute_matches_reference(name):
+    """`impute` (bayes_net.py:877-908) on 25 partial samples per example network (2-3 missing
+    variables; with one the reference itself fails, see oracle/gen_golden.py)."""
+    golden = load_golden(name)
+    net = oracle_net(_example(golden["network"]))
+    for case in golden["cases"]:
+        sample = {k: v for k, v in case["sample"]}
+        want = {k: v for k, v in case["filled"]}
+        assert ve_oracle.impute(net, sample) == want, case
+
+
+@pytest.mark.parametrize("name", golden_names(("gibbs_conditionals",)))
+def test_oracle_gibbs_conditionals_match_reference(name):
+    """The deterministic half of `_gibbs_sampling`: P(var | Markov boundary) for every variable
+    (bayes_net.py:699-712), entry by entry, including which configurations the reference drops."""
+    golden = load_golden(name)
+    net = oracle_net(_example(golden["network"]))
+    for node, g in golden["nodes"].items():
+        boundary, table = ve_oracle.gibbs_conditional(net, node)
+        assert boundary == g["boundary"], (node, boundary, g["boundary"])
+        pos = [{v: i for i, v in enumerate(net.domains[u])} for u in [*boundary, node]]
+        seen = np.zeros(table.shape, dtype=bool)
+        for key, want in zip(g["index"], g["values"]):
+            idx = tuple(pos[i][k] for i, k in enumerate(key))
+            seen[idx] = True
+            assert abs(table[idx] - want) <= 1e-12 * max(want, 1e-300), (node, key, table[idx], want)
+        # what the reference leaves out is exactly what is zero (or undefined: 0/0) here
+        rest = table[~seen]
+        assert np.all((rest == 0) | np.isnan(rest)), (node, rest)
+
+
+def test_reference_copy_driven_in_min_fill_order_matches_the_oracle():
+    """`oracle/_ref` (the reference itself, copied by oracle/build_ref.py) driven through
+    oracle/ref_driver.ordered_query -- what bench.py's CPU legs time -- gives the oracle's
+    posterior.  Skipped where the copy was not built."""
+    from oracle import build_ref, ref_driver
+    from sorobn_b200 import planner, synthetic
+
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    import warnings
+
+    ref = build_ref.import_reference()
+    from sorobn_b200 import BayesNet
+
+    spec = synthetic.grid(4, 4, 3, seed=11)
+    ours = synthetic.load(spec, BayesNet)
+    theirs = synthetic.load(spec, ref.BayesNet)
+    net = ours._compiled
+    query, evs = ("g0303",), ("g0001", "g0102", "g0203", "g0300")
+    plan = planner.build_plan(net, [net.index[q] for q in query], [net.index[e] for e in evs])
+    order = [net.names[v] for v in plan.order]
+    dn = oracle_net(ours)
+    events = synthetic.random_events(spec, evs, 3, seed=5)
+    for b in range(len(events)):
+        event = {v: int(events[v].iloc[b]) for v in evs}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = ref_driver.ordered_query(ref, theirs, query, event, order)
+        want = ve_oracle.query(dn, *query, event=event)[1].reshape(-1)
+        dense = np.zeros_like(want)
+        for k, v in got.items():
+            dense[dn.domains[query[0]].index(k)] = v
+        assert np.allclose(dense, want, rtol=1e-12, atol=0)

@@ -72,3 +72,57 @@ def test_two_rank_gloo_sharding_matches_single_rank(tmp_path, n_rows):
     got = np.load(out)
     assert got.shape == (2, n_rows)
     assert np.allclose(got.sum(axis=0), 1.0, atol=1e-6)
+
+
+class _OracleProgram:
+    """Stand-in for engine.Program on the CPU ranks (tests may use the oracle as the engine)."""
+
+    def __init__(self):
+        from oracle import ve_oracle
+        from sorobn_b200 import workloads
+
+        self.wl = workloads.asia_1m()
+        self.bn = self.wl.build()
+        self.net = self.bn._compiled
+        self.dn = ve_oracle.dense_from_pandas(self.bn.P, self.bn.parents, self.bn.nodes)
+        self.ve = ve_oracle
+
+    def run(self, codes, n):
+        out = np.zeros((2, n), dtype=np.float32)
+        for b in range(n):
+            ev = {v: self.net.domains[self.net.index[v]][codes[i, b]] for i, v in enumerate(self.wl.evidence)}
+            out[:, b] = self.ve.query(self.dn, *self.wl.query, event=ev)[1].reshape(-1)
+        return out
+
+
+def _sharded_program_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prog = _OracleProgram()
+        counts = [9, 6]  # ragged: rank 1 has fewer rows than rows_max
+        sp = sharding.ShardedProgram(prog, Q=2, n_ev=4, rows_max=max(counts), dst=0)
+        codes = prog.wl.codes(prog.bn, counts[rank], seed=100 + rank)  # every rank has its own rows
+        for _ in range(2):  # buffers are reused between calls
+            got = sp.run_host(codes, counts[rank], counts=counts)
+        if rank == 0:
+            want = np.concatenate([prog.run(prog.wl.codes(prog.bn, counts[r], seed=100 + r), counts[r])
+                                   for r in range(world)], axis=1)
+            assert got.shape == (2, sum(counts)) and np.array_equal(got, want)
+            np.save(out_path, got)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_program_gathers_ragged_rank_batches(tmp_path):
+    """The torchrun path bench.py --gpus N drives (sharding.ShardedProgram), over gloo with the
+    oracle as the per-rank engine: every rank answers its own rows, rank 0 gets them in rank order."""
+    out = str(tmp_path / "sp.npy")
+    mp.spawn(_sharded_program_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    assert got.shape == (2, 15) and np.allclose(got.sum(axis=0), 1.0, atol=1e-6)
