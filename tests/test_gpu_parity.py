@@ -593,3 +593,61 @@ def test_sliced_staging_of_big_cpts_matches_the_oracle():
         want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
         worst = max(worst, rel_err(tiled[:, b], want))
     assert worst < RTOL, worst
+
+
+@pytest.mark.parametrize("name", golden_names(("impute",)))
+def test_impute_matches_reference_goldens(name):
+    """`impute` (bayes_net.py:877-908) pinned to the reference's own results (2-3 missing values
+    per sample), one sample at a time and as one `impute_many` batch (mixed missing patterns)."""
+    from sorobn_b200 import examples
+
+    golden = load_golden(name)
+    bn = examples.build(examples.NETWORKS[golden["network"]])
+    rows = []
+    for case in golden["cases"]:
+        sample = {k: v for k, v in case["sample"]}
+        want = {k: v for k, v in case["filled"]}
+        got = bn.impute(dict(sample))
+        assert {k: got[k] for k in want} == want, (sample, dict(got), want)
+        rows.append(sample)
+    frame = pd.DataFrame(rows, dtype=object)
+    filled = bn.impute_many(frame)
+    for b, case in enumerate(golden["cases"]):
+        want = {k: v for k, v in case["filled"]}
+        assert {k: filled[k].iloc[b] for k in want} == want, (b, filled.iloc[b].to_dict(), want)
+
+
+def test_query_many_over_a_device_list_equals_the_single_device_answer():
+    """`query_many(devices=[...])` shards the rows over the listed GPUs from one process (one
+    thread and one program per device); with every visible device it must return exactly what
+    the default single-device call returns -- ragged shards, float64 rescue included."""
+    from sorobn_b200 import engine, workloads
+
+    wl = workloads.asia_1m()
+    bn = wl.build()
+    events = wl.events(10_007, seed=3, bn=bn)
+    want = bn.query_many(*wl.query, events=events)
+    n_dev = engine.device_count()
+    for devices in ([0], list(range(n_dev)), [0] * 3):  # the same GPU three times: three programs, three threads
+        got = bn.query_many(*wl.query, events=events, devices=devices)
+        pd.testing.assert_frame_equal(got, want, check_exact=True)
+
+
+def test_program_chunk_capacity_grows_with_the_batch():
+    """A cached program first used for ONE row must not answer a later large batch one row at a
+    time: the reservation follows the largest batch seen."""
+    from sorobn_b200 import workloads
+
+    wl = workloads.asia_1m()
+    bn = wl.build()
+    events = wl.events(50_000, seed=5, bn=bn)
+    first = bn.query_many(*wl.query, events=events.iloc[:1])
+    _, program = bn._plan(wl.query, tuple(events.columns), 1)
+    assert program.info()["reserved_rows"] >= 1
+    full = bn.query_many(*wl.query, events=events)
+    assert program.info()["reserved_rows"] >= 50_000
+    assert np.array_equal(full.iloc[:1].to_numpy(), first.to_numpy())
+    launches = program.info()["launches"]
+    bn.query_many(*wl.query, events=events)
+    per_call = program.info()["launches"] - launches
+    assert per_call <= 4, per_call  # one chunk: a couple of launches, not 50,000 rounds
