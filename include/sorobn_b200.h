@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 6
+#define SBN_ABI_VERSION 7
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -112,7 +112,9 @@ int sbn_program_profile(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, i
 
 /* info[0]=Q  [1]=n_ev  [2]=n_steps  [3]=scratch floats per row  [4]=reserved rows
  * [5]=kernel launches issued by this program so far  [6]=mode (0 flat, 1 batched)
- * [7]=unbatched scratch floats */
+ * [7]=unbatched scratch floats
+ * with n_info >= 12 also: [8]=on-chip segments in use  [9]=steps they cover  [10]=bytes per row the
+ * segments still move through the HBM slot arena  [11]=per-CTA private scratch floats */
 int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 
 /* 0 = plain launches; 1 = CUDA-graph replay of the step sequence (default); 3 = graph replay
@@ -123,7 +125,10 @@ int sbn_program_set_graph(sbn_program *prog, int enabled);
 /* Select the step kernel: 0 = the plain one-output-per-iteration kernel (general
  * fallback, cross-check in tests); 1 or 2 = register-tiled kernel with the operand
  * preload schedule where available (default); 4 = tiled, x-loop schedule only; 5 = tiled
- * without the shared-memory slab variant for expanding products. */
+ * without the shared-memory slab variant for expanding products; 7 = run the on-chip segments
+ * (csrc/sbn_chain.h: runs of steps executed by one persistent kernel with the intermediates in
+ * shared memory / an L2-resident scratch; opt-in, also SOROBN_B200_CHAIN=1), 6 = back to one launch
+ * per step. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* ------------------------------------------------------------------ Gibbs sampling

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "sbn_chain.h"
 #include "sbn_gibbs.cuh"
 #include "sbn_internal.h"
 #include "sbn_kernels.cuh"
@@ -919,6 +920,10 @@ cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64
 // every later run reads their outputs (19 of the 67 launches of the benchmark grid's step).
 inline bool hoisted(const sbn_program *P, const StepDesc &st) { return P->mode == 1 && st.kind == 0; }
 
+inline bool chain_on(const sbn_program *P) {
+    return P->use_chain && P->chain_fits && P->use_tiled && !P->use_branches && !P->segments.empty();
+}
+
 int run_table_steps(sbn_program *P) {
     if (P->mode != 1) return SBN_OK;
     SbnStep q;
@@ -941,11 +946,19 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
         if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
         ++k;
         if (hoisted(P, st)) continue;  // computed once, when the program was created
+        const int seg = chain_on(P) ? P->seg_first[k - 1] : -1;
+        if (seg == -2) continue;       // runs inside the segment launched at its first step
+        if (seg >= 0) {
+            P->launches++;
+            SBN_CUDA(sbn_chain_launch(P, *P->segments[seg], d_ev, ld_ev, n_rows, d_out, ld_out, stream));
+            continue;
+        }
         build_params(P, st, d_ev, ld_ev, n_rows, &q);
         SBN_CUDA(launch_step(P, st, q, stream));
     }
     if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
-    SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, stream));
+    if (!(chain_on(P) && !P->segments.empty() && P->segments.back()->ends_in_posterior))
+        SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, stream));
     if (events) SBN_CUDA(cudaEventRecord(events[k + 1], stream));
     return SBN_OK;
 }
@@ -1055,6 +1068,10 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
     sbn_program *P = new sbn_program();
     P->device = device;
     P->f64 = f64;
+    {
+        const char *e = getenv("SOROBN_B200_CHAIN");
+        P->use_chain = e && atoi(e) != 0;  // on-chip segments are opt-in (see sbn_chain.cu)
+    }
     const size_t elem = f64 ? 8 : 4;
     int rc = parse(P, words, n_words);
 
@@ -1120,15 +1137,16 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
             }
     }
     {
-        std::vector<int32_t> tile_words;
+        std::vector<int32_t> &tile_words = P->h_tile_words;  // kept: sbn_chain_bind derives its byte tables from them
+        tile_words.clear();
         plan_tiles(P, &tile_words);
         if (!tile_words.empty()) {
             SBN_CUDA_P(cudaMalloc(&P->d_tile_off, tile_words.size() * 4));
             SBN_CUDA_P(cudaMemcpyAsync(P->d_tile_off, tile_words.data(), tile_words.size() * 4,
                                        cudaMemcpyHostToDevice, P->stream));
         }
-        // tile_words goes out of scope here: the copy must have consumed it
         SBN_CUDA_P(cudaStreamSynchronize(P->stream));
+        sbn_chain_plan(P);
     }
     {
         // opt every step-kernel instantiation into SBN_SMEM_BUDGET of dynamic shared memory
@@ -1144,6 +1162,7 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
             SBN_CUDA_P(set_smem_attr_n<7>());
             SBN_CUDA_P(set_smem_attr_n<8>());
             SBN_CUDA_P(set_tiled_attrs());
+            SBN_CUDA_P(sbn_chain_set_attrs());
             done[device] = true;
         }
     }
@@ -1168,6 +1187,7 @@ void sbn_program_destroy(sbn_program *P) {
     if (!P) return;
     cudaSetDevice(P->device);
     free_scratch(P);
+    sbn_chain_free(P);
     cudaFree(P->d_shared);
     cudaFree(P->d_tile_off);
     cudaFree(P->d_tables);
@@ -1222,6 +1242,7 @@ int sbn_program_reserve(sbn_program *P, int64_t max_rows) {
     SBN_CUDA(cudaStreamSynchronize(P->stream));  // the memset must not race a caller's stream
     P->reserved_rows = rows;
     P->ld = ld;
+    SBN_CUDA(sbn_chain_bind(P));  // segment descriptors point into the new arena
     return SBN_OK;
 }
 
@@ -1360,7 +1381,19 @@ int sbn_program_profile(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int6
 }
 
 int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
-    if (!P || !info || n_info < 8) return fail(SBN_E_INVALID, "info needs 8 entries");
+    if (!P || !info || n_info < 8) return fail(SBN_E_INVALID, "info needs at least 8 entries");
+    if (n_info >= 12) {
+        int64_t covered = 0, hbm = 0, scratch = 0;
+        for (const SbnSegment *seg : P->segments) {
+            covered += static_cast<int64_t>(seg->steps.size());
+            hbm += seg->hbm_bytes_per_row;
+            scratch = std::max(scratch, seg->scratch_floats);
+        }
+        info[8] = chain_on(P) ? static_cast<int64_t>(P->segments.size()) : 0;
+        info[9] = chain_on(P) ? covered : 0;
+        info[10] = chain_on(P) ? hbm : 0;
+        info[11] = scratch;
+    }
     info[0] = P->Q;
     info[1] = P->n_ev;
     info[2] = static_cast<int64_t>(P->steps.size());
@@ -1395,6 +1428,8 @@ int sbn_program_set_tiled(sbn_program *P, int enabled) {
     P->use_tiled = enabled != 0;
     P->use_preload = enabled != 4;
     P->use_slab = enabled != 5;
+    if (enabled == 6) P->use_chain = false;
+    if (enabled == 7) P->use_chain = true;
     return SBN_OK;
 }
 

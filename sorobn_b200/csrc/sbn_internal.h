@@ -104,5 +104,13 @@ struct sbn_program {
 
     int64_t launches = 0;
     int64_t setup_launches = 0;  // evidence-independent launches issued once at creation
+
+    // on-chip segments (sbn_chain.h): runs of batched steps executed by one persistent kernel
+    std::vector<SbnSegment *> segments;
+    std::vector<int> seg_first;      // per step: >= 0 = head of that segment, -2 = inside one, -1 = classic launch
+    float *d_chain_scratch = nullptr;
+    bool use_chain = true;
+    bool chain_fits = true;          // false when a slot-arena operand of a segment needs > 32-bit byte offsets
+    std::vector<int32_t> h_tile_words;  // host copy of d_tile_off
 };
 

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class EngineError(RuntimeError):
@@ -186,14 +186,16 @@ class Program:
         _check(load().sbn_program_set_graph(self._h, int(bool(enabled))))
 
     def set_tiled(self, mode):
-        """False/0: plain kernel; True/1: tiled (default); 2 or 4: tiled with that many rows per thread."""
+        """0: plain kernel; 1: tiled (default); 4: tiled, x-loop schedule only; 5: no slab variant;
+        7: on-chip segments on (csrc/sbn_chain.h, opt-in); 6: off again."""
         _check(load().sbn_program_set_tiled(self._h, int(mode)))
 
     def info(self) -> dict:
-        buf = (ctypes.c_int64 * 8)()
-        _check(load().sbn_program_info(self._h, buf, 8))
+        buf = (ctypes.c_int64 * 12)()
+        _check(load().sbn_program_info(self._h, buf, 12))
         keys = ("Q", "n_ev", "n_steps", "scratch_floats_per_row", "reserved_rows", "launches", "mode",
-                "shared_scratch_floats")
+                "shared_scratch_floats", "segments", "segment_steps", "segment_hbm_bytes_per_row",
+                "segment_scratch_floats")
         return dict(zip(keys, [int(x) for x in buf]))
 
     # --------------------------------------------------------------------- runs

@@ -493,6 +493,8 @@ def build_plan(net: CompiledNet, query, evidence, mode=MODE_BATCHED, order=None,
 
     steps = _merge_sum_outs(steps, merge_sum_outs)
     if mode == MODE_BATCHED:
+        if os.environ.get("SOROBN_B200_DFS", "1") == "1":
+            steps = _depth_first_order(steps)
         _relayout_big_tables(steps, table_arrays, table_axes, evidence, card)
     slots, post_slot = _assign_slots(steps, post.buf, keep_unbatched=(mode == MODE_BATCHED))
 
@@ -582,6 +584,46 @@ def _merge_sum_outs(steps, enabled=True):
         merged.append(st)
         producer[st.out_id] = len(merged) - 1
     return merged
+
+
+def _depth_first_order(steps):
+    """Re-order the launches depth first.
+
+    The steps form a tree (every intermediate has exactly one consumer, the last step produces
+    the posterior); the elimination order interleaves its branches.  Executing one branch to the
+    end before starting the next keeps the fewest intermediates alive -- the children of a step
+    are visited in decreasing (peak - result) order, which is optimal for trees (Sethi-Ullman) --
+    so the engine's on-chip segments (csrc/sbn_chain.h) can hold them in shared memory, and a run
+    of `frontier <- sum table x frontier` steps becomes contiguous.  Any topological order gives
+    the same numbers; slots are assigned afterwards, for THIS order."""
+    by_id = {st.out_id: i for i, st in enumerate(steps)}
+    children = []
+    for st in steps:
+        children.append([by_id[f.buf] for f, _, _ in st.inputs if f.is_slot])
+    size = [int(np.prod(st.cards, dtype=np.int64)) if st.kind == KIND_BATCHED else 0 for st in steps]
+    peak = [0] * len(steps)
+    order_of = [None] * len(steps)
+    # children always precede their consumer in the incoming list: one forward pass suffices
+    for i, st in enumerate(steps):
+        kids = sorted(children[i], key=lambda c: (-(peak[c] - size[c]), c))
+        held, worst = 0, 0
+        for c in kids:
+            worst = max(worst, held + peak[c])
+            held += size[c]
+        peak[i] = max(worst, held + size[i])
+        order_of[i] = kids
+    out, stack = [], [(len(steps) - 1, 0)]
+    seen = set()
+    while stack:  # iterative post-order
+        node, k = stack.pop()
+        if k < len(order_of[node]):
+            stack.append((node, k + 1))
+            stack.append((order_of[node][k], 0))
+        elif node not in seen:
+            seen.add(node)
+            out.append(steps[node])
+    assert len(out) == len(steps), "a step does not feed the posterior"
+    return out
 
 
 def _assign_slots(steps, post_id, keep_unbatched=False):

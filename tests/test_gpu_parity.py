@@ -651,3 +651,45 @@ def test_program_chunk_capacity_grows_with_the_batch():
     bn.query_many(*wl.query, events=events)
     per_call = program.info()["launches"] - launches
     assert per_call <= 4, per_call  # one chunk: a couple of launches, not 50,000 rounds
+
+
+@pytest.mark.parametrize("workload,rows", [("grid10x10", 4099), ("asia_1m", 10_001), ("dag50", 3001)])
+def test_on_chip_segments_match_classic_launches_and_the_oracle(workload, rows):
+    """The segment kernel (csrc/sbn_chain.cu: runs of steps executed on chip for 32 rows at a time,
+    intermediates in shared memory / L2-resident scratch, fused normalisation) against the classic
+    one-launch-per-step path on the same program, at a ragged row count (partial row block, more
+    row blocks than CTAs), and against the oracle on a sample of rows."""
+    from oracle import ve_oracle
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.WORKLOADS[workload]()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    codes = wl.codes(bn, rows, seed=21)
+    prog = engine.Program(plan)
+    assert prog.info()["segments"] == 0  # opt-in: the default is one launch per step
+    prog.set_tiled(7)
+    info = prog.info()
+    if workload == "grid10x10":
+        assert info["segments"] >= 1 and info["segment_steps"] >= 40 and info["segment_hbm_bytes_per_row"] == 0, info
+    chained = prog.run(codes, rows).copy()
+    again = prog.run(codes, rows)
+    assert np.array_equal(chained, again, equal_nan=True)  # deterministic
+    prog.set_tiled(6)
+    assert prog.info()["segments"] == 0
+    classic = prog.run(codes, rows)
+    assert np.isfinite(classic).all()
+    assert np.allclose(chained, classic, rtol=3e-6, atol=1e-30)
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    order = [net.names[v] for v in plan.order]
+    for b in list(range(0, rows, max(1, rows // 7))) + [rows - 1]:
+        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        assert rel_err(chained[:, b], want) < RTOL, (b, chained[:, b], want)
+    # P(event) per row comes out of the fused normalisation too
+    prog.set_tiled(7)
+    p_chain = prog.evidence(codes, rows)
+    prog.set_tiled(6)
+    p_classic = prog.evidence(codes, rows)
+    assert np.allclose(p_chain, p_classic, rtol=3e-6, atol=0)

@@ -20,6 +20,8 @@ prog = engine.Program(plan)
 prog.set_graph(False)
 if os.environ.get("SBN_PLAIN"):
     prog.set_tiled(False)
+if os.environ.get("SBN_CHAIN"):
+    prog.set_tiled(7)
 codes = wl.codes(bn, rows, seed=1000)
 d_ev = torch.from_numpy(codes).cuda()
 d_out = torch.empty((prog.Q, rows), dtype=torch.float32, device="cuda")
