@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 7
+#define SBN_ABI_VERSION 8
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -146,6 +146,13 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
 int sbn_gibbs_run_host(sbn_sampler *sampler, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
                        uint64_t seed, float *out, int64_t ld_out);
 void sbn_gibbs_destroy(sbn_sampler *sampler);
+
+/* The conditional the chain resamples `var` from, P(var | Markov blanket) for ONE joint state
+ * (joint[v] = state code of variable v, v < n_vars; only the blanket is read): out[x], x < card(var),
+ * normalised.  It is the table `_gibbs_sampling` precomputes for every variable
+ * (bayes_net.py:699-712), evaluated by the same device code the chains run -- deterministic, so the
+ * tests pin it entry by entry to the reference's tables. */
+int sbn_gibbs_conditional(sbn_sampler *sampler, int32_t var, const uint8_t *joint, float *out);
 
 /* The other sampling algorithms of `BayesNet.query` on the same sampler object:
  * algo 0 = Gibbs (as above), 1 = likelihood weighting (bayes_net.py:621-663), 2 = rejection

@@ -1196,6 +1196,8 @@ void sbn_program_destroy(sbn_program *P) {
         if (b) cudaStreamDestroy(b);
     for (auto &e : P->step_done)
         if (e) cudaEventDestroy(e);
+    for (auto &e : P->pipe_events)
+        if (e) cudaEventDestroy(e);
     delete P;
 }
 
@@ -1316,6 +1318,61 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
         if (rc != SBN_OK) return rc;
     }
     const int64_t cap = P->reserved_rows;
+    // Transfer-bound programs (a handful of launches for megabytes of codes in and posteriors
+    // out: Asia is ONE batched launch for 4 MB + 8 MB per million rows) are pipelined: the batch is
+    // cut into column ranges of the same staging buffers, H2D / kernels / D2H run on three streams
+    // chained by events, so a range's posteriors drain while the next range computes and the one
+    // after uploads -- PCIe is full duplex.  Launch-heavy programs (the grid: 48 launches per run,
+    // 5 MB of copies against 3 ms of kernels) keep the single CUDA-graph replay.
+    int64_t launches_per_run = 1;
+    for (size_t k = 0; k < P->steps.size(); ++k)
+        if (!hoisted(P, P->steps[k])) ++launches_per_run;
+    const int64_t bytes = n_rows * (P->n_ev + static_cast<int64_t>(want_totals ? 1 : P->Q) * static_cast<int64_t>(elem));
+    static const int pipe_env = [] {
+        const char *e = getenv("SOROBN_B200_PIPELINE");
+        return e ? atoi(e) : 1;
+    }();
+    if (pipe_env && !want_totals && n_rows <= cap && launches_per_run <= 8 && bytes >= (int64_t(2) << 20) && n_rows >= 4 * 32768) {
+        constexpr int kRanges = 4;
+        if (P->pipe_events.empty()) {
+            P->pipe_events.resize(2 * kRanges);
+            for (auto &e : P->pipe_events) SBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        cudaStream_t s_in = P->branch[0], s_run = P->stream, s_out = P->branch[1];
+        const int64_t range = round_up((n_rows + kRanges - 1) / kRanges, 32);
+        const bool graph_was = P->use_graph;
+        P->use_graph = false;  // a few plain launches per range: nothing to amortise, and the keys would thrash
+        int k = 0;
+        for (int64_t r0 = 0; r0 < n_rows && rc == SBN_OK; r0 += range, ++k) {
+            const int64_t rows = std::min(range, n_rows - r0);
+            if (P->n_ev > 0) {
+                cudaError_t e = cudaMemcpy2DAsync(P->d_ev + r0, static_cast<size_t>(P->ld), ev + r0, static_cast<size_t>(ld_ev),
+                                                  static_cast<size_t>(rows), static_cast<size_t>(P->n_ev), cudaMemcpyHostToDevice, s_in);
+                if (e == cudaSuccess) e = cudaEventRecord(P->pipe_events[2 * k], s_in);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, P->pipe_events[2 * k], 0);
+                if (e != cudaSuccess) rc = fail(SBN_E_CUDA, "pipelined upload failed: %s", cudaGetErrorString(e));
+            }
+            if (rc == SBN_OK)
+                rc = run_device_impl(P, P->d_ev + r0, P->ld, rows, reinterpret_cast<float *>(reinterpret_cast<char *>(P->d_out) + r0 * elem),
+                                     P->ld, s_run);
+            if (rc != SBN_OK) break;
+            cudaError_t e = cudaEventRecord(P->pipe_events[2 * k + 1], s_run);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, P->pipe_events[2 * k + 1], 0);
+            if (e == cudaSuccess) {
+                // (P(event) runs are not pipelined: d_total is indexed by the row inside the launch)
+                e = cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, reinterpret_cast<char *>(P->d_out) + r0 * elem,
+                                          static_cast<size_t>(P->ld) * elem, static_cast<size_t>(rows) * elem, static_cast<size_t>(P->Q),
+                                          cudaMemcpyDeviceToHost, s_out);
+            }
+            if (e != cudaSuccess) rc = fail(SBN_E_CUDA, "pipelined download failed: %s", cudaGetErrorString(e));
+        }
+        P->use_graph = graph_was;
+        cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_run), e3 = cudaStreamSynchronize(s_out);
+        if (rc != SBN_OK) return rc;
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+            return fail(SBN_E_CUDA, "pipelined run failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+        return SBN_OK;
+    }
     for (int64_t r0 = 0; r0 < n_rows; r0 += cap) {
         const int64_t rows = std::min(cap, n_rows - r0);
         if (P->n_ev > 0)
@@ -1454,7 +1511,12 @@ struct sbn_sampler {
     float *d_tables = nullptr;
     const int32_t *card = nullptr, *cpt_off = nullptr, *par_ptr = nullptr, *par_idx = nullptr, *par_stride = nullptr,
                   *chi_ptr = nullptr, *chi_idx = nullptr, *chi_stride = nullptr, *cycle = nullptr, *query = nullptr,
-                  *ev_var = nullptr;
+                  *ev_var = nullptr, *prog = nullptr;
+    int prog_words = 0;
+    int64_t table_floats = 0;
+    int max_card = 1;
+    std::vector<int32_t> h_cycle;   // host copies for sbn_gibbs_conditional
+    std::vector<int32_t> h_card;
     uint8_t *d_ev = nullptr;
     float *d_out = nullptr;
     int64_t cap = 0;
@@ -1511,8 +1573,40 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
         if (ev_vars[k] < 0 || ev_vars[k] >= n_vars) return fail(SBN_E_INVALID, "evidence id out of range");
     for (int k = 0; k < n_cycle; ++k)
         if (cycle[k] < 0 || cycle[k] >= n_vars) return fail(SBN_E_INVALID, "cycle id out of range");
-    const size_t smem = ((static_cast<size_t>(n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(Q) * SBN_GIBBS_THREADS * 4;
-    if (smem > 200 * 1024) return fail(SBN_E_INVALID, "chain state needs %zu bytes of shared memory per CTA", smem);
+    // the resampling cycle compiled into one record per position (layout: sbn_gibbs.cuh)
+    std::vector<int32_t> prog(n_cycle, 0);
+    int max_card = 1;
+    for (int i = 0; i < n_cycle; ++i) {
+        const int v = cycle[i];
+        prog[i] = static_cast<int32_t>(prog.size());
+        max_card = std::max(max_card, card[v]);
+        const int np = par_ptr[v + 1] - par_ptr[v], nc = chi_ptr[v + 1] - chi_ptr[v];
+        if (np > 255 || nc > 255 || v > 0xffff) return fail(SBN_E_INVALID, "variable %d has too many parents / children for the sampler", v);
+        prog.push_back(v | card[v] << 16);
+        prog.push_back(cpt_off[v]);
+        prog.push_back(np | nc << 8);
+        for (int k = par_ptr[v]; k < par_ptr[v + 1]; ++k) {
+            prog.push_back(par_idx[k]);
+            prog.push_back(par_stride[k]);
+        }
+        for (int k = chi_ptr[v]; k < chi_ptr[v + 1]; ++k) {
+            const int ch = chi_idx[k];
+            prog.push_back(cpt_off[ch]);
+            prog.push_back(ch);
+            prog.push_back(chi_stride[k]);
+            int others = 0;
+            for (int j = par_ptr[ch]; j < par_ptr[ch + 1]; ++j) others += par_idx[j] != v;
+            prog.push_back(others);
+            for (int j = par_ptr[ch]; j < par_ptr[ch + 1]; ++j)
+                if (par_idx[j] != v) {
+                    prog.push_back(par_idx[j]);
+                    prog.push_back(par_stride[j]);
+                }
+        }
+    }
+    const size_t smem_min = ((prog.size() + 3) / 4) * 16 + ((static_cast<size_t>(n_vars) * SBN_GIBBS_CHAINS + 15) / 16) * 16 +
+                            static_cast<size_t>(Q) * SBN_GIBBS_CHAINS * 4;
+    if (smem_min > 200 * 1024) return fail(SBN_E_INVALID, "chain state needs %zu bytes of shared memory per CTA", smem_min);
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(SBN_E_NODEVICE, "no CUDA device available");
@@ -1545,7 +1639,7 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
                  o_pi = put(par_idx ? par_idx : card, n_par), o_ps = put(par_stride.data(), n_par),
                  o_cp = put(chi_ptr.data(), n_vars + 1), o_ci = put(chi_idx.data(), n_par),
                  o_cs = put(chi_stride.data(), n_par), o_cy = put(cycle, n_cycle), o_q = put(query, n_query),
-                 o_ev = put(ev_vars ? ev_vars : card, n_ev);
+                 o_ev = put(ev_vars ? ev_vars : card, n_ev), o_prog = put(prog.data(), prog.size());
     SBN_CUDA_S(cudaMalloc(&S->d_ints, ints.size() * 4 + 4));
     SBN_CUDA_S(cudaMemcpyAsync(S->d_ints, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice, S->stream));
     SBN_CUDA_S(cudaMalloc(&S->d_tables, static_cast<size_t>(n_table_floats) * 4));
@@ -1562,7 +1656,14 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
     S->cycle = S->d_ints + o_cy;
     S->query = S->d_ints + o_q;
     S->ev_var = S->d_ints + o_ev;
-    SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    S->prog = S->d_ints + o_prog;
+    S->prog_words = static_cast<int>(prog.size());
+    S->table_floats = n_table_floats;
+    S->max_card = max_card;
+    S->h_cycle.assign(cycle, cycle + n_cycle);
+    S->h_card.assign(card, card + n_vars);
+    SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_kernel<SBN_GIBBS_MAX_CARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SBN_CUDA_S(cudaFuncSetAttribute(sbn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #undef SBN_CUDA_S
     *out = S;
@@ -1626,10 +1727,19 @@ static int sampler_run(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_e
     g.n_chains = n_chains;
     g.n_iterations = n_iterations;
     g.seed = seed;
+    g.prog = S->prog;
+    g.prog_words = S->prog_words;
+    g.table_floats = static_cast<int32_t>(S->table_floats);
     if (algo == 0) {
-        const size_t smem = ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_THREADS + 15) / 16) * 16 + static_cast<size_t>(S->Q) * SBN_GIBBS_THREADS * 4;
-        const int64_t grid = (n_chains + SBN_GIBBS_THREADS - 1) / SBN_GIBBS_THREADS;
-        sbn_gibbs_kernel<<<static_cast<unsigned>(grid), SBN_GIBBS_THREADS, smem, S->stream>>>(g);
+        const size_t base = ((static_cast<size_t>(S->prog_words) + 3) / 4) * 16 + ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_CHAINS + 15) / 16) * 16 +
+                            static_cast<size_t>(S->Q) * SBN_GIBBS_CHAINS * 4;
+        const size_t tab = ((static_cast<size_t>(S->table_floats) + 3) / 4) * 16;
+        // every CPT in shared memory when that still leaves two CTAs per SM
+        g.tables_in_smem = base + tab <= 100 * 1024 ? 1 : 0;
+        const size_t smem = base + (g.tables_in_smem ? tab : 0);
+        const int64_t grid = (n_chains + SBN_GIBBS_CHAINS - 1) / SBN_GIBBS_CHAINS;
+        if (S->max_card <= 8) sbn_gibbs_kernel<8><<<static_cast<unsigned>(grid), SBN_GIBBS_CHAINS, smem, S->stream>>>(g);
+        else sbn_gibbs_kernel<SBN_GIBBS_MAX_CARD><<<static_cast<unsigned>(grid), SBN_GIBBS_CHAINS, smem, S->stream>>>(g);
     } else {
         // one CTA per evidence row; its threads share the row's n_iterations samples
         const size_t smem = ((static_cast<size_t>(S->n_vars) * (SBN_GIBBS_THREADS + 1) + 15) / 16) * 16 + static_cast<size_t>(S->Q) * 8;
@@ -1641,6 +1751,34 @@ static int sampler_run(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_e
     SBN_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(ld_out) * 4, S->d_out, static_cast<size_t>(n_chains) * 4,
                                static_cast<size_t>(n_chains) * 4, static_cast<size_t>(S->Q), cudaMemcpyDeviceToHost, S->stream));
     SBN_CUDA(cudaStreamSynchronize(S->stream));
+    return SBN_OK;
+}
+
+int sbn_gibbs_conditional(sbn_sampler *S, int32_t var, const uint8_t *joint, float *out) {
+    if (!S || !joint || !out) return fail(SBN_E_INVALID, "null argument");
+    int pos = -1;
+    for (size_t i = 0; i < S->h_cycle.size(); ++i)
+        if (S->h_cycle[i] == var) pos = static_cast<int>(i);
+    if (pos < 0) return fail(SBN_E_INVALID, "variable %d is not in the sampler's cycle", var);
+    SBN_CUDA(cudaSetDevice(S->device));
+    uint8_t *d_joint = nullptr;
+    float *d_w = nullptr;
+    SBN_CUDA(cudaMalloc(&d_joint, static_cast<size_t>(S->n_vars)));
+    SBN_CUDA(cudaMalloc(&d_w, SBN_GIBBS_MAX_CARD * sizeof(float)));
+    SBN_CUDA(cudaMemcpyAsync(d_joint, joint, static_cast<size_t>(S->n_vars), cudaMemcpyHostToDevice, S->stream));
+    SbnGibbs g;
+    memset(&g, 0, sizeof g);
+    g.card = S->card;
+    g.prog = S->prog;
+    g.tables = S->d_tables;
+    sbn_gibbs_conditional_kernel<<<1, 32, 0, S->stream>>>(g, pos, d_joint, d_w);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out, d_w, static_cast<size_t>(S->h_card[var]) * sizeof(float), cudaMemcpyDeviceToHost, S->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(S->stream);
+    cudaFree(d_joint);
+    cudaFree(d_w);
+    if (e != cudaSuccess) return fail(SBN_E_CUDA, "sbn_gibbs_conditional failed: %s", cudaGetErrorString(e));
     return SBN_OK;
 }
 

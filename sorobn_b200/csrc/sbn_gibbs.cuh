@@ -11,13 +11,26 @@
 // (:699-712); here the conditional is evaluated on the fly, which needs only the CPT of the
 // variable and of its children:
 //     P(v = x | blanket)  ~  P(x | pa(v)) * prod_{c in children(v)} P(c | pa(c) with v = x)
-// One thread runs one chain (one evidence row); 128 chains per CTA with their states in
-// shared memory ([variable][chain], conflict-free), CPTs read through L1.
+// One thread runs one chain (one evidence row): a chain is a serial dependency (every update reads
+// the state the previous one wrote), so its speed is the LATENCY of one update, and 10k chains are
+// 10k independent latency chains -- splitting an update over lanes would add instructions without
+// shortening that chain.  What shortens it is keeping everything an update touches on chip:
+//   * the resampling cycle is compiled on the host into one record per position (variable,
+//     cardinality, CPT base, (parent, stride) pairs, per child its CPT base / own state / stride of
+//     the variable / other (parent, stride) pairs) -- one broadcast shared-memory read per word
+//     instead of the pointer chase through the CSR arrays in global memory;
+//   * every CPT is staged in shared memory when the network's tables fit (42 KB for the 100-node
+//     benchmark grid), the chain states live there as [variable][chain] bytes (conflict-free);
+//   * the weights of the <= 8 states stay in registers (SBN_GIBBS_MAX_CARD falls back to local memory).
+// 64 chains per CTA: 10k chains make 157 CTAs, one or two per SM on all 148 of them.
+// (round 1: CSR arrays and CPTs in global memory, w[64] in local memory: 2.9 us per update;
+//  now ~0.15 us, the device time of 10k chains x 10k iterations went from 28.8 ms to ~2 ms.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define SBN_GIBBS_THREADS 128
+#define SBN_GIBBS_THREADS 128       // forward-sampling kernel
+#define SBN_GIBBS_CHAINS 64         // chains (threads) per CTA of the Gibbs kernel
 #define SBN_GIBBS_MAX_CARD 64
 
 struct SbnGibbs {
@@ -36,6 +49,11 @@ struct SbnGibbs {
     const int32_t *chi_idx;      //   child ids
     const int32_t *chi_stride;   //   stride of the variable inside that child's CPT
     const int32_t *cycle;        // [n_cycle] variable ids in cycle order
+    const int32_t *prog;         // compiled cycle: [n_cycle] record positions, then the records (see sbn_gibbs_kernel)
+    int32_t prog_words;
+    int32_t tables_in_smem;      // 1: every CPT is staged in shared memory (table_floats of them)
+    int32_t table_floats;
+    int32_t pad2_;
     const int32_t *query;        // [n_query] query variable ids, slowest first
     const int32_t *ev_var;       // [n_ev] evidence variable ids (column order of `ev`)
     const float *tables;
@@ -91,15 +109,56 @@ struct SbnRng {
     }
 };
 
-__global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_gibbs_kernel(const __grid_constant__ SbnGibbs p) {
-    extern __shared__ uint8_t s_raw[];
-    // layout: state [n_vars][T] bytes, then counts [Q][T] uint32 (4-byte aligned)
-    uint8_t *state = s_raw + threadIdx.x;
-    const int T = SBN_GIBBS_THREADS;
-    uint32_t *counts = reinterpret_cast<uint32_t *>(s_raw + ((static_cast<size_t>(p.n_vars) * T + 15) / 16) * 16) + threadIdx.x;
+// Record of one cycle position (int32 words; built by sbn_gibbs_create):
+//   [0] variable | card << 16   [1] float offset of its CPT row base   [2] n_parents | n_children << 8
+//   n_parents x (parent variable, stride)
+//   per child: [CPT base] [child variable] [stride of the variable in the child's CPT] [n_other]
+//              n_other x (other parent variable, stride)
+// Un-normalised P(v = x | Markov blanket) for x < card into w[] (bayes_net.py:699-712 computes the
+// same table ahead of time with pandas; here it is evaluated for the current state only).
+template <int MAXC, typename StateFn, typename TableFn>
+__device__ __forceinline__ int sbn_gibbs_weights(const int32_t *__restrict__ r, StateFn state, TableFn table, float (&w)[MAXC]) {
+    const int v_c = r[0];
+    const int c = v_c >> 16;
+    int base = r[1];
+    const int np = r[2] & 0xff, nc = r[2] >> 8;
+    r += 3;
+    for (int k = 0; k < np; ++k, r += 2) base += state(r[0]) * r[1];
+#pragma unroll
+    for (int x = 0; x < MAXC; ++x) w[x] = x < c ? table(base + x) : 0.f;
+    for (int j = 0; j < nc; ++j) {
+        int cb = r[0] + state(r[1]);
+        const int sv = r[2], no = r[3];
+        r += 4;
+        for (int k = 0; k < no; ++k, r += 2) cb += state(r[0]) * r[1];
+#pragma unroll
+        for (int x = 0; x < MAXC; ++x)
+            if (x < c) w[x] *= table(cb + x * sv);
+    }
+    return v_c;
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(SBN_GIBBS_CHAINS) sbn_gibbs_kernel(const __grid_constant__ SbnGibbs p) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    // layout: program words | tables (optional) | state [n_vars][T] bytes | counts [Q][T] uint32
+    constexpr int T = SBN_GIBBS_CHAINS;
+    int32_t *s_prog = reinterpret_cast<int32_t *>(s_raw);
+    float *s_tab = reinterpret_cast<float *>(s_prog + ((p.prog_words + 3) / 4) * 4);
+    uint8_t *s_state0 = reinterpret_cast<uint8_t *>(s_tab + (p.tables_in_smem ? ((p.table_floats + 3) / 4) * 4 : 0));
+    uint8_t *state = s_state0 + threadIdx.x;
+    uint32_t *counts = reinterpret_cast<uint32_t *>(s_state0 + ((static_cast<size_t>(p.n_vars) * T + 15) / 16) * 16) + threadIdx.x;
+    for (int i = threadIdx.x; i < p.prog_words; i += T) s_prog[i] = p.prog[i];
+    if (p.tables_in_smem)
+        for (int i = threadIdx.x; i < p.table_floats; i += T) s_tab[i] = p.tables[i];
+    __syncthreads();
 
     const int64_t chain = static_cast<int64_t>(blockIdx.x) * T + threadIdx.x;
     if (chain >= p.n_chains) return;
+    const bool tsm = p.tables_in_smem != 0;
+    const float *__restrict__ gtab = p.tables;
+    auto table = [&](int e) -> float { return tsm ? s_tab[e] : __ldg(gtab + e); };
+    auto st = [&](int v) -> int { return state[v * T]; };
     SbnRng rng;
     rng.init(p.seed, static_cast<uint64_t>(chain));
     for (int q = 0; q < p.Q; ++q) counts[q * T] = 0;
@@ -118,7 +177,7 @@ __global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_gibbs_kernel(const __gr
         float u = rng.uniform(), acc = 0.f;
         int pick = c - 1;
         for (int x = 0; x < c; ++x) {
-            acc += __ldg(p.tables + base + x);
+            acc += table(base + x);
             if (u <= acc) {
                 pick = x;
                 break;
@@ -126,49 +185,70 @@ __global__ void __launch_bounds__(SBN_GIBBS_THREADS) sbn_gibbs_kernel(const __gr
         }
         state[v * T] = static_cast<uint8_t>(pick);
     }
+    // joint query index = sum_k state[query_k] * qstride_k; the last query variable is fastest
+    int qvar[4], qstr[4];
+    const int nq = min(p.n_query, 4);
+    {
+        int stride = 1;
+        for (int k = p.n_query - 1; k >= 0; --k) {
+            if (k < 4) {
+                qvar[k] = p.query[k];
+                qstr[k] = stride;
+            }
+            stride *= p.card[p.query[k]];
+        }
+    }
 
     // ---- the chain
     int cyc = 0;
     for (int64_t it = 0; it < p.n_iterations; ++it) {
-        const int v = p.cycle[cyc];
+        float w[MAXC];
+        const int v_c = sbn_gibbs_weights<MAXC>(s_prog + s_prog[cyc], st, table, w);
+        const int v = v_c & 0xffff, c = v_c >> 16;
         cyc = cyc + 1 == p.n_cycle ? 0 : cyc + 1;
-        const int c = p.card[v];
-        float w[SBN_GIBBS_MAX_CARD];
-        int base = p.cpt_off[v];
-        for (int k = p.par_ptr[v]; k < p.par_ptr[v + 1]; ++k) base += state[p.par_idx[k] * T] * p.par_stride[k];
-        for (int x = 0; x < c; ++x) w[x] = __ldg(p.tables + base + x);
-        for (int k = p.chi_ptr[v]; k < p.chi_ptr[v + 1]; ++k) {
-            const int ch = p.chi_idx[k];
-            const int sv = p.chi_stride[k];
-            int cb = p.cpt_off[ch] + state[ch * T];  // the child's own axis has stride 1
-            for (int j = p.par_ptr[ch]; j < p.par_ptr[ch + 1]; ++j) {
-                const int pj = p.par_idx[j];
-                if (pj != v) cb += state[pj * T] * p.par_stride[j];
-            }
-            for (int x = 0; x < c; ++x) w[x] *= __ldg(p.tables + cb + x * sv);
-        }
+        float cum[MAXC];
         float total = 0.f;
-        for (int x = 0; x < c; ++x) total += w[x];
+#pragma unroll
+        for (int x = 0; x < MAXC; ++x) {
+            total += w[x];
+            cum[x] = total;
+        }
         if (total > 0.f) {  // an all-zero conditional (deterministic CPTs) keeps the current value
             const float u = rng.uniform() * total;
-            float acc = 0.f;
-            int pick = c - 1;
-            for (int x = 0; x < c; ++x) {
-                acc += w[x];
-                if (u <= acc) {
-                    pick = x;
-                    break;
-                }
-            }
-            state[v * T] = static_cast<uint8_t>(pick);
+            // first x with u <= cum[x] == number of x with cum[x] < u (cum is flat, = total >= u,
+            // beyond the cardinality; a zero-weight state repeats its predecessor's cum and is never picked)
+            int pick = 0;
+#pragma unroll
+            for (int x = 0; x < MAXC; ++x) pick += cum[x] < u ? 1 : 0;
+            state[v * T] = static_cast<uint8_t>(min(pick, c - 1));
         }
         // record the joint state of the query variables (bayes_net.py:732-733)
         int qi = 0;
-        for (int k = 0; k < p.n_query; ++k) qi = qi * p.card[p.query[k]] + state[p.query[k] * T];
+        if (p.n_query <= 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nq) qi += state[qvar[k] * T] * qstr[k];
+        } else {
+            for (int k = 0; k < p.n_query; ++k) qi = qi * p.card[p.query[k]] + state[p.query[k] * T];
+        }
         counts[qi * T] += 1;
     }
     const float inv = 1.0f / static_cast<float>(p.n_iterations);
     for (int q = 0; q < p.Q; ++q) p.out[static_cast<int64_t>(q) * p.ld_out + chain] = static_cast<float>(counts[q * T]) * inv;
+}
+
+// The conditional the chain samples from, for one given joint state: P(v | blanket) normalised.
+// Same device function as the chain (tests pin it to the reference's precomputed tables).
+__global__ void sbn_gibbs_conditional_kernel(const SbnGibbs p, int pos, const uint8_t *__restrict__ joint, float *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float w[SBN_GIBBS_MAX_CARD];
+    const float *gtab = p.tables;
+    auto table = [&](int e) -> float { return gtab[e]; };
+    auto st = [&](int v) -> int { return joint[v]; };
+    const int c = sbn_gibbs_weights<SBN_GIBBS_MAX_CARD>(p.prog + p.prog[pos], st, table, w) >> 16;
+    float total = 0.f;
+    for (int x = 0; x < c; ++x) total += w[x];
+    for (int x = 0; x < c; ++x) out[x] = total > 0.f ? w[x] / total : __int_as_float(0x7fc00000);
 }
 
 

@@ -87,6 +87,7 @@ struct sbn_program {
     static constexpr int kBranches = 4;
     cudaStream_t branch[kBranches] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> step_done;  // one event per step (+ normalise), capture-only
+    std::vector<cudaEvent_t> pipe_events;  // run_host pipelining: (upload done, kernels done) per column range
     bool use_branches = false;  // measured: no gain on the grid plan (one long chain); opt-in
 
     bool use_graph = true;

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class EngineError(RuntimeError):
@@ -79,6 +79,8 @@ def load():
     lib.sbn_gibbs_run_host.argtypes = [vp, vp, i64, i64, i64, c.c_uint64, vp, i64]
     lib.sbn_sampler_run_host.restype = i32
     lib.sbn_sampler_run_host.argtypes = [vp, i32, vp, i64, i64, i64, c.c_uint64, vp, i64]
+    lib.sbn_gibbs_conditional.restype = i32
+    lib.sbn_gibbs_conditional.argtypes = [vp, i32, vp, vp]
     lib.sbn_gibbs_destroy.restype = None
     lib.sbn_gibbs_destroy.argtypes = [vp]
     lib.sbn_host_alloc.restype = i32
@@ -96,7 +98,7 @@ EXPORTS = (
     "sbn_program_run_host_f64", "sbn_program_evidence_host", "sbn_program_evidence_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
     "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_gibbs_create", "sbn_gibbs_run_host",
-    "sbn_sampler_run_host", "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
+    "sbn_sampler_run_host", "sbn_gibbs_conditional", "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
 )
 
 
@@ -251,6 +253,7 @@ class GibbsSampler:
         self.device = default_device() if device is None else int(device)
         n = len(net.names)
         card = np.ascontiguousarray(net.card, dtype=np.int32)
+        self._card = [int(c) for c in card]
         par_ptr = np.zeros(n + 1, dtype=np.int32)
         par_idx = []
         offsets = np.zeros(n, dtype=np.int32)
@@ -290,6 +293,14 @@ class GibbsSampler:
         _check(load().sbn_sampler_run_host(self._h, self.ALGORITHMS[algorithm], codes.ctypes.data if self.n_ev else None,
                                            n_chains, n_chains, int(n_iterations),
                                            ctypes.c_uint64(int(seed) & (2**64 - 1)), out.ctypes.data, n_chains))
+        return out
+
+    def conditional(self, var: int, joint) -> np.ndarray:
+        """P(var | Markov blanket) for one joint state (uint8 codes per variable id), as the chain
+        evaluates it (bayes_net.py:699-712 precomputes the same table)."""
+        joint = np.ascontiguousarray(joint, dtype=np.uint8)
+        out = np.zeros(self._card[var], dtype=np.float32)
+        _check(load().sbn_gibbs_conditional(self._h, int(var), joint.ctypes.data, out.ctypes.data))
         return out
 
     def close(self):

@@ -675,7 +675,9 @@ def test_on_chip_segments_match_classic_launches_and_the_oracle(workload, rows):
         assert info["segments"] >= 1 and info["segment_steps"] >= 40 and info["segment_hbm_bytes_per_row"] == 0, info
     chained = prog.run(codes, rows).copy()
     again = prog.run(codes, rows)
-    assert np.array_equal(chained, again, equal_nan=True)  # deterministic
+    # (not bitwise: a step with few tiles and many eliminated states splits them over warps whose
+    # partial sums meet through atomic adds, in arrival order)
+    assert np.allclose(chained, again, rtol=1e-6, atol=1e-30)
     prog.set_tiled(6)
     assert prog.info()["segments"] == 0
     classic = prog.run(codes, rows)
@@ -693,3 +695,31 @@ def test_on_chip_segments_match_classic_launches_and_the_oracle(workload, rows):
     prog.set_tiled(6)
     p_classic = prog.evidence(codes, rows)
     assert np.allclose(p_chain, p_classic, rtol=3e-6, atol=0)
+
+
+def test_pipelined_host_path_equals_the_device_path():
+    """`sbn_program_run_host` pipelines transfer-bound programs (Asia: one batched launch for
+    megabytes of codes and posteriors): column ranges on three streams.  The answer must be
+    bitwise the one of a single device-resident run, also for a ragged row count."""
+    import torch
+
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.asia_1m()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    prog = engine.Program(plan)
+    rows = 400_003
+    codes = wl.codes(bn, rows, seed=9)
+    host = prog.run(codes, rows)  # >= 4 x 32768 rows and >= 2 MB of copies: pipelined
+    d_ev = torch.from_numpy(codes).cuda()
+    d_out = torch.empty((prog.Q, rows), dtype=torch.float32, device="cuda")
+    prog.run_device(d_ev.data_ptr(), rows, rows, d_out.data_ptr(), rows, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(host, d_out.cpu().numpy())
+    assert np.allclose(host.sum(axis=0), 1.0, atol=1e-5)
+    again = prog.run(codes, rows)
+    assert np.array_equal(host, again)
+    small = prog.run(np.ascontiguousarray(codes[:, :1000]), 1000)  # below the threshold: single-stream path
+    assert np.array_equal(small, host[:, :1000])
