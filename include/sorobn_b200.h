@@ -162,6 +162,7 @@ int sbn_gibbs_conditional(sbn_sampler *sampler, int32_t var, const uint8_t *join
 #define SBN_ALGO_GIBBS 0
 #define SBN_ALGO_LIKELIHOOD 1
 #define SBN_ALGO_REJECTION 2
+#define SBN_ALGO_GIBBS_GENERIC 3  /* Gibbs through the generic kernel even when the straight-line one applies (tests) */
 int sbn_sampler_run_host(sbn_sampler *sampler, int algo, const uint8_t *ev, int64_t ld_ev, int64_t n_rows,
                          int64_t n_iterations, uint64_t seed, float *out, int64_t ld_out);
 

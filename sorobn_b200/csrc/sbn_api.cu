@@ -515,6 +515,10 @@ void free_scratch(sbn_program *P) {
         cudaGraphExecDestroy(P->exec);
         P->exec = nullptr;
     }
+    if (P->pipe_exec) {
+        cudaGraphExecDestroy(P->pipe_exec);
+        P->pipe_exec = nullptr;
+    }
     cudaFree(P->d_arena);
     cudaFree(P->d_ev);
     cudaFree(P->d_out);
@@ -923,6 +927,8 @@ inline bool hoisted(const sbn_program *P, const StepDesc &st) { return P->mode =
 inline bool chain_on(const sbn_program *P) {
     return P->use_chain && P->chain_fits && P->use_tiled && !P->use_branches && !P->segments.empty();
 }
+
+inline bool graph_allowed(const sbn_program *P) { return P->use_graph; }
 
 int run_table_steps(sbn_program *P) {
     if (P->mode != 1) return SBN_OK;
@@ -1335,42 +1341,96 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
     if (pipe_env && !want_totals && n_rows <= cap && launches_per_run <= 8 && bytes >= (int64_t(2) << 20) && n_rows >= 4 * 32768) {
         constexpr int kRanges = 4;
         if (P->pipe_events.empty()) {
-            P->pipe_events.resize(2 * kRanges);
+            P->pipe_events.resize(3 + 2 * kRanges);
             for (auto &e : P->pipe_events) SBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         cudaStream_t s_in = P->branch[0], s_run = P->stream, s_out = P->branch[1];
         const int64_t range = round_up((n_rows + kRanges - 1) / kRanges, 32);
-        const bool graph_was = P->use_graph;
-        P->use_graph = false;  // a few plain launches per range: nothing to amortise, and the keys would thrash
-        int k = 0;
-        for (int64_t r0 = 0; r0 < n_rows && rc == SBN_OK; r0 += range, ++k) {
-            const int64_t rows = std::min(range, n_rows - r0);
-            if (P->n_ev > 0) {
-                cudaError_t e = cudaMemcpy2DAsync(P->d_ev + r0, static_cast<size_t>(P->ld), ev + r0, static_cast<size_t>(ld_ev),
-                                                  static_cast<size_t>(rows), static_cast<size_t>(P->n_ev), cudaMemcpyHostToDevice, s_in);
-                if (e == cudaSuccess) e = cudaEventRecord(P->pipe_events[2 * k], s_in);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, P->pipe_events[2 * k], 0);
-                if (e != cudaSuccess) rc = fail(SBN_E_CUDA, "pipelined upload failed: %s", cudaGetErrorString(e));
+        // the whole fan-out is issued into a stream capture and replayed as ONE graph launch when the
+        // host buffers are pinned (a dozen copies, launches and event edges cost more CPU time than
+        // the 0.2 ms they overlap); the graph is kept for the (buffers, rows) it was built for
+        auto pinned = [](const void *ptr) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
             }
-            if (rc == SBN_OK)
+            return a.type == cudaMemoryTypeHost;
+        };
+        const bool as_graph = graph_allowed(P) && pinned(out) && (P->n_ev == 0 || pinned(ev));
+        auto &key = P->pipe_key;
+        const bool hit = as_graph && P->pipe_exec && key.ev == ev && key.ld_ev == ld_ev && key.n_rows == n_rows && key.out == out &&
+                         key.ld_out == ld_out;
+        if (!hit) {
+            if (P->pipe_exec) {
+                cudaGraphExecDestroy(P->pipe_exec);
+                P->pipe_exec = nullptr;
+            }
+            const bool graph_was = P->use_graph;
+            P->use_graph = false;  // a few plain launches per range: nothing to amortise inside
+            cudaError_t e = cudaSuccess;
+            if (as_graph) {
+                e = cudaStreamBeginCapture(s_run, cudaStreamCaptureModeRelaxed);
+                if (e == cudaSuccess) e = cudaEventRecord(P->pipe_events[0], s_run);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_in, P->pipe_events[0], 0);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, P->pipe_events[0], 0);
+            }
+            const int64_t before = P->launches;
+            int k = 0;
+            for (int64_t r0 = 0; r0 < n_rows && rc == SBN_OK && e == cudaSuccess; r0 += range, ++k) {
+                const int64_t rows = std::min(range, n_rows - r0);
+                cudaEvent_t up = P->pipe_events[1 + 2 * k], done = P->pipe_events[2 + 2 * k];
+                if (P->n_ev > 0) {
+                    e = cudaMemcpy2DAsync(P->d_ev + r0, static_cast<size_t>(P->ld), ev + r0, static_cast<size_t>(ld_ev),
+                                          static_cast<size_t>(rows), static_cast<size_t>(P->n_ev), cudaMemcpyHostToDevice, s_in);
+                    if (e == cudaSuccess) e = cudaEventRecord(up, s_in);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, up, 0);
+                    if (e != cudaSuccess) break;
+                }
                 rc = run_device_impl(P, P->d_ev + r0, P->ld, rows, reinterpret_cast<float *>(reinterpret_cast<char *>(P->d_out) + r0 * elem),
                                      P->ld, s_run);
-            if (rc != SBN_OK) break;
-            cudaError_t e = cudaEventRecord(P->pipe_events[2 * k + 1], s_run);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, P->pipe_events[2 * k + 1], 0);
-            if (e == cudaSuccess) {
+                if (rc != SBN_OK) break;
+                e = cudaEventRecord(done, s_run);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, done, 0);
                 // (P(event) runs are not pipelined: d_total is indexed by the row inside the launch)
-                e = cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, reinterpret_cast<char *>(P->d_out) + r0 * elem,
+                if (e == cudaSuccess)
+                    e = cudaMemcpy2DAsync(out + r0 * elem, static_cast<size_t>(ld_out) * elem, reinterpret_cast<char *>(P->d_out) + r0 * elem,
                                           static_cast<size_t>(P->ld) * elem, static_cast<size_t>(rows) * elem, static_cast<size_t>(P->Q),
                                           cudaMemcpyDeviceToHost, s_out);
             }
-            if (e != cudaSuccess) rc = fail(SBN_E_CUDA, "pipelined download failed: %s", cudaGetErrorString(e));
+            P->use_graph = graph_was;
+            if (as_graph) {
+                // join the side streams back into the origin, end the capture
+                cudaEvent_t j_in = P->pipe_events[1 + 2 * kRanges], j_out = P->pipe_events[2 + 2 * kRanges];
+                if (e == cudaSuccess) e = cudaEventRecord(j_in, s_in);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, j_in, 0);
+                if (e == cudaSuccess) e = cudaEventRecord(j_out, s_out);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, j_out, 0);
+                cudaGraph_t graph = nullptr;
+                const cudaError_t e_end = cudaStreamEndCapture(s_run, &graph);
+                P->pipe_launches = P->launches - before;
+                P->launches = before;
+                if (e == cudaSuccess) e = e_end;
+                if (e == cudaSuccess && rc == SBN_OK) e = cudaGraphInstantiate(&P->pipe_exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (rc != SBN_OK) return rc;
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(SBN_E_CUDA, "pipelined graph capture failed: %s", cudaGetErrorString(e));
+                }
+                key = {ev, ld_ev, n_rows, out, ld_out};
+            } else {
+                cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_run), e3 = cudaStreamSynchronize(s_out);
+                if (rc != SBN_OK) return rc;
+                if (e != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+                    return fail(SBN_E_CUDA, "pipelined run failed: %s",
+                                cudaGetErrorString(e != cudaSuccess ? e : e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+                return SBN_OK;
+            }
         }
-        P->use_graph = graph_was;
-        cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_run), e3 = cudaStreamSynchronize(s_out);
-        if (rc != SBN_OK) return rc;
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
-            return fail(SBN_E_CUDA, "pipelined run failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+        SBN_CUDA(cudaGraphLaunch(P->pipe_exec, s_run));
+        P->launches += P->pipe_launches;
+        SBN_CUDA(cudaStreamSynchronize(s_run));
         return SBN_OK;
     }
     for (int64_t r0 = 0; r0 < n_rows; r0 += cap) {
@@ -1511,8 +1571,8 @@ struct sbn_sampler {
     float *d_tables = nullptr;
     const int32_t *card = nullptr, *cpt_off = nullptr, *par_ptr = nullptr, *par_idx = nullptr, *par_stride = nullptr,
                   *chi_ptr = nullptr, *chi_idx = nullptr, *chi_stride = nullptr, *cycle = nullptr, *query = nullptr,
-                  *ev_var = nullptr, *prog = nullptr;
-    int prog_words = 0;
+                  *ev_var = nullptr, *prog = nullptr, *flat = nullptr;
+    int prog_words = 0, flat_words = 0;
     int64_t table_floats = 0;
     int max_card = 1;
     std::vector<int32_t> h_cycle;   // host copies for sbn_gibbs_conditional
@@ -1604,6 +1664,51 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
                 }
         }
     }
+    // the straight-line variant (sbn_gibbs_flat_kernel): fixed-size records, when the network is small enough
+    std::vector<int32_t> flat;
+    bool flat_ok = max_card <= 8 && n_query <= 4 && n_vars < 0xffff;
+    const int32_t ones_off = static_cast<int32_t>(n_table_floats);  // a 1.0f appended to the table blob
+    for (int i = 0; i < n_cycle && flat_ok; ++i) {
+        const int v = cycle[i];
+        const int np = par_ptr[v + 1] - par_ptr[v], nc = chi_ptr[v + 1] - chi_ptr[v];
+        if (np > SBN_GF_TERMS || nc > SBN_GF_GROUPS - 1) { flat_ok = false; break; }
+        std::vector<int32_t> rec(SBN_GF_WORDS, 0);
+        rec[0] = v | card[v] << 16;
+        auto group = [&](int g) { return rec.data() + 2 + g * (2 + 2 * SBN_GF_TERMS); };
+        for (int g = 0; g < SBN_GF_GROUPS; ++g) {  // padding: the constant 1.0, terms on the dummy state
+            int32_t *gw = group(g);
+            gw[0] = ones_off;
+            gw[1] = 0;
+            for (int k = 0; k < SBN_GF_TERMS; ++k) { gw[2 + 2 * k] = n_vars; gw[3 + 2 * k] = 0; }
+        }
+        int32_t *g0 = group(0);
+        g0[0] = cpt_off[v];
+        g0[1] = 1;
+        for (int k = par_ptr[v], t = 0; k < par_ptr[v + 1]; ++k, ++t) { g0[2 + 2 * t] = par_idx[k]; g0[3 + 2 * t] = par_stride[k]; }
+        for (int k = chi_ptr[v], g = 1; k < chi_ptr[v + 1] && flat_ok; ++k, ++g) {
+            const int ch = chi_idx[k];
+            int32_t *gw = group(g);
+            gw[0] = cpt_off[ch];
+            gw[1] = chi_stride[k];
+            int t = 0;
+            gw[2] = ch;  // the child's own state, stride 1
+            gw[3] = 1;
+            ++t;
+            for (int j = par_ptr[ch]; j < par_ptr[ch + 1]; ++j)
+                if (par_idx[j] != v) {
+                    if (t >= SBN_GF_TERMS) { flat_ok = false; break; }
+                    gw[2 + 2 * t] = par_idx[j];
+                    gw[3 + 2 * t] = par_stride[j];
+                    ++t;
+                }
+        }
+        flat.insert(flat.end(), rec.begin(), rec.end());
+    }
+    if (flat_ok) {
+        const size_t need = flat.size() * 4 + ((static_cast<size_t>(n_table_floats) + 1 + 3) / 4) * 16 +
+                            ((static_cast<size_t>(n_vars + 1) * SBN_GIBBS_CHAINS + 15) / 16) * 16 + static_cast<size_t>(Q) * SBN_GIBBS_CHAINS * 4;
+        if (need > 100 * 1024) flat_ok = false;  // two CTAs per SM
+    }
     const size_t smem_min = ((prog.size() + 3) / 4) * 16 + ((static_cast<size_t>(n_vars) * SBN_GIBBS_CHAINS + 15) / 16) * 16 +
                             static_cast<size_t>(Q) * SBN_GIBBS_CHAINS * 4;
     if (smem_min > 200 * 1024) return fail(SBN_E_INVALID, "chain state needs %zu bytes of shared memory per CTA", smem_min);
@@ -1640,10 +1745,16 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
                  o_cp = put(chi_ptr.data(), n_vars + 1), o_ci = put(chi_idx.data(), n_par),
                  o_cs = put(chi_stride.data(), n_par), o_cy = put(cycle, n_cycle), o_q = put(query, n_query),
                  o_ev = put(ev_vars ? ev_vars : card, n_ev), o_prog = put(prog.data(), prog.size());
+    while (ints.size() % 4) ints.push_back(0);  // the flat records are read as int4
+    const size_t o_flat = put(flat.data(), flat_ok ? flat.size() : 0);
     SBN_CUDA_S(cudaMalloc(&S->d_ints, ints.size() * 4 + 4));
     SBN_CUDA_S(cudaMemcpyAsync(S->d_ints, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice, S->stream));
-    SBN_CUDA_S(cudaMalloc(&S->d_tables, static_cast<size_t>(n_table_floats) * 4));
+    SBN_CUDA_S(cudaMalloc(&S->d_tables, static_cast<size_t>(n_table_floats + 1) * 4));
     SBN_CUDA_S(cudaMemcpyAsync(S->d_tables, tables, static_cast<size_t>(n_table_floats) * 4, cudaMemcpyHostToDevice, S->stream));
+    {
+        static const float one = 1.0f;  // the padding entry of the straight-line records
+        SBN_CUDA_S(cudaMemcpyAsync(S->d_tables + n_table_floats, &one, 4, cudaMemcpyHostToDevice, S->stream));
+    }
     SBN_CUDA_S(cudaStreamSynchronize(S->stream));
     S->card = S->d_ints + o_card;
     S->cpt_off = S->d_ints + o_off;
@@ -1658,6 +1769,9 @@ int sbn_gibbs_create(int device, int32_t n_vars, const int32_t *card, const int3
     S->ev_var = S->d_ints + o_ev;
     S->prog = S->d_ints + o_prog;
     S->prog_words = static_cast<int>(prog.size());
+    S->flat = flat_ok ? S->d_ints + o_flat : nullptr;
+    S->flat_words = flat_ok ? static_cast<int>(flat.size()) : 0;
+    SBN_CUDA_S(cudaFuncSetAttribute(sbn_gibbs_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     S->table_floats = n_table_floats;
     S->max_card = max_card;
     S->h_cycle.assign(cycle, cycle + n_cycle);
@@ -1684,6 +1798,8 @@ void sbn_gibbs_destroy(sbn_sampler *S) {
 static int sampler_run(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_ev, int64_t n_chains, int64_t n_iterations,
                        uint64_t seed, float *out, int64_t ld_out) {
     if (!S || !out) return fail(SBN_E_INVALID, "null argument");
+    const bool force_generic = algo == 3;  // Gibbs through the generic kernel (cross-check of the straight-line one)
+    if (algo == 3) algo = 0;
     if (algo < 0 || algo > 2) return fail(SBN_E_INVALID, "unknown sampling algorithm %d", algo);
     if (n_chains <= 0 || n_iterations <= 0) return fail(SBN_E_INVALID, "n_chains and n_iterations must be positive");
     if (S->n_ev > 0 && (!ev || (S->n_ev > 1 && ld_ev < n_chains))) return fail(SBN_E_INVALID, "bad evidence");
@@ -1730,7 +1846,20 @@ static int sampler_run(sbn_sampler *S, int algo, const uint8_t *ev, int64_t ld_e
     g.prog = S->prog;
     g.prog_words = S->prog_words;
     g.table_floats = static_cast<int32_t>(S->table_floats);
-    if (algo == 0) {
+    static const bool flat_env = [] {
+        const char *e = getenv("SOROBN_B200_GIBBS_FLAT");
+        return e ? atoi(e) != 0 : true;
+    }();
+    if (algo == 0 && S->flat && flat_env && !force_generic) {
+        g.prog = S->flat;
+        g.prog_words = S->flat_words;
+        g.table_floats = static_cast<int32_t>(S->table_floats + 1);
+        g.tables_in_smem = 1;
+        const size_t smem = static_cast<size_t>(S->flat_words) * 4 + ((static_cast<size_t>(g.table_floats) + 3) / 4) * 16 +
+                            ((static_cast<size_t>(S->n_vars + 1) * SBN_GIBBS_CHAINS + 15) / 16) * 16 + static_cast<size_t>(S->Q) * SBN_GIBBS_CHAINS * 4;
+        const int64_t grid = (n_chains + SBN_GIBBS_CHAINS - 1) / SBN_GIBBS_CHAINS;
+        sbn_gibbs_flat_kernel<<<static_cast<unsigned>(grid), SBN_GIBBS_CHAINS, smem, S->stream>>>(g);
+    } else if (algo == 0) {
         const size_t base = ((static_cast<size_t>(S->prog_words) + 3) / 4) * 16 + ((static_cast<size_t>(S->n_vars) * SBN_GIBBS_CHAINS + 15) / 16) * 16 +
                             static_cast<size_t>(S->Q) * SBN_GIBBS_CHAINS * 4;
         const size_t tab = ((static_cast<size_t>(S->table_floats) + 3) / 4) * 16;

@@ -87,7 +87,15 @@ struct sbn_program {
     static constexpr int kBranches = 4;
     cudaStream_t branch[kBranches] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> step_done;  // one event per step (+ normalise), capture-only
-    std::vector<cudaEvent_t> pipe_events;  // run_host pipelining: (upload done, kernels done) per column range
+    std::vector<cudaEvent_t> pipe_events;  // run_host pipelining: fork, (upload done, kernels done) per column range, joins
+    cudaGraphExec_t pipe_exec = nullptr;   // the pipelined host run as one graph (pinned host buffers)
+    struct {
+        const void *ev;
+        int64_t ld_ev, n_rows;
+        const void *out;
+        int64_t ld_out;
+    } pipe_key = {nullptr, 0, 0, nullptr, 0};
+    int64_t pipe_launches = 0;
     bool use_branches = false;  // measured: no gain on the grid plan (one long chain); opt-in
 
     bool use_graph = true;

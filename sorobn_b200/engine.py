@@ -281,7 +281,7 @@ class GibbsSampler:
             self.n_ev, self.evidence.ctypes.data if self.n_ev else None, len(cycle), cycle.ctypes.data,
             ctypes.byref(self._h)))
 
-    ALGORITHMS = {"gibbs": 0, "likelihood": 1, "rejection": 2}
+    ALGORITHMS = {"gibbs": 0, "likelihood": 1, "rejection": 2, "gibbs_generic": 3}
 
     def run(self, codes: np.ndarray, n_chains: int, n_iterations: int, seed: int, algorithm: str = "gibbs") -> np.ndarray:
         """uint8 codes [n_ev, n_rows] -> estimated posterior float32 [Q, n_rows] (one Gibbs

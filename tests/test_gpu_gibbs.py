@@ -197,3 +197,20 @@ def test_every_algorithm_answers_like_the_reference_check_query():
     many = examples.alarm(seed=2).query_many("Alarm", events=pd.DataFrame({"John calls": [True, False, True]}),
                                              algorithm="likelihood", n_iterations=20_000)
     assert many.shape == (3, 2) and np.allclose(many.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_straight_line_gibbs_kernel_equals_the_generic_one_bit_for_bit():
+    """Small networks run the chain through fixed-size records (sbn_gibbs_flat_kernel); same random
+    stream, same arithmetic as the generic kernel, so the frequencies must be identical."""
+    from sorobn_b200 import engine, workloads
+
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    cycle = [net.index[v] for v in sorted(set(bn.nodes) - set(wl.evidence))]
+    sampler = engine.GibbsSampler(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence], cycle)
+    codes = wl.codes(bn, 777, seed=3)
+    flat = sampler.run(codes, 777, 3001, seed=99, algorithm="gibbs")
+    generic = sampler.run(codes, 777, 3001, seed=99, algorithm="gibbs_generic")
+    assert np.array_equal(flat, generic)
+    assert np.allclose(flat.sum(axis=0), 1.0, atol=1e-5)
