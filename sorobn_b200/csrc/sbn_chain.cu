@@ -573,6 +573,8 @@ int64_t step_table_floats(const sbn_program *P, const StepDesc &st) {
 bool chainable(const sbn_program *P, const StepDesc &st, int64_t tab_max) {
     if (st.kind != 1 || st.tile <= 0 || st.big_tables || st.slice_pos >= 0) return false;
     if (st.nu > 2 || st.na > 2 || st.nb > 2 || st.nc > 1 || st.in.size() > 4) return false;
+    static const int min_out = env_int("SOROBN_B200_CHAIN_MINOUT", 0), max_out = env_int("SOROBN_B200_CHAIN_MAXOUT", 1 << 30);
+    if (st.n_out < min_out || st.n_out > max_out) return false;  // experiments: segments of big-frontier steps only
     return step_table_floats(P, st) <= tab_max;
 }
 
