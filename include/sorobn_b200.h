@@ -128,7 +128,9 @@ int sbn_program_set_graph(sbn_program *prog, int enabled);
  * without the shared-memory slab variant for expanding products; 7 = run the on-chip segments
  * (csrc/sbn_chain.h: runs of steps executed by one persistent kernel with the intermediates in
  * shared memory / an L2-resident scratch; opt-in, also SOROBN_B200_CHAIN=1), 6 = back to one launch
- * per step. */
+ * per step; 9 = run the steps it covers through the tensor-map TMA pipeline kernel (csrc/sbn_tma.h: 2-D / 4-D
+ * `cp.async.bulk.tensor` boxes into a shared-memory ring fed by a producer warp; opt-in, also SOROBN_B200_TMA=1:
+ * parity-green but not faster than the register-preload kernel), 8 = off again. */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* ------------------------------------------------------------------ Gibbs sampling

@@ -19,6 +19,7 @@
 #include "sbn_gibbs.cuh"
 #include "sbn_internal.h"
 #include "sbn_kernels.cuh"
+#include "sbn_tma.h"
 
 namespace {
 
@@ -859,6 +860,8 @@ cudaError_t set_tiled_attrs() {
 
 cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cudaStream_t stream) {
     P->launches++;
+    if (st.kind == 1 && q.tile_off != nullptr && sbn_tma_eligible(P, st))
+        return sbn_tma_launch(P, st, q.ev, q.ld_ev, q.n_rows, stream);
     if (st.kind == 1 && q.tile_off != nullptr) {
         const int64_t chunks = (q.n_tiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
         const int64_t grid = chunks * q.n_bblocks;
@@ -1077,6 +1080,8 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
     {
         const char *e = getenv("SOROBN_B200_CHAIN");
         P->use_chain = e && atoi(e) != 0;  // on-chip segments are opt-in (see sbn_chain.cu)
+        e = getenv("SOROBN_B200_TMA");
+        P->use_tma = e && atoi(e) != 0;    // so is the tensor-map TMA pipeline kernel (see sbn_tma.cu: no gain measured)
     }
     const size_t elem = f64 ? 8 : 4;
     int rc = parse(P, words, n_words);
@@ -1169,6 +1174,7 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
             SBN_CUDA_P(set_smem_attr_n<8>());
             SBN_CUDA_P(set_tiled_attrs());
             SBN_CUDA_P(sbn_chain_set_attrs());
+            SBN_CUDA_P(sbn_tma_set_attrs());
             done[device] = true;
         }
     }
@@ -1545,6 +1551,8 @@ int sbn_program_set_tiled(sbn_program *P, int enabled) {
     P->use_tiled = enabled != 0;
     P->use_preload = enabled != 4;
     P->use_slab = enabled != 5;
+    if (enabled == 8) P->use_tma = false;
+    if (enabled == 9) P->use_tma = true;
     if (enabled == 6) P->use_chain = false;
     if (enabled == 7) P->use_chain = true;
     return SBN_OK;

@@ -119,6 +119,7 @@ struct sbn_program {
     std::vector<int> seg_first;      // per step: >= 0 = head of that segment, -2 = inside one, -1 = classic launch
     float *d_chain_scratch = nullptr;
     bool use_chain = true;
+    bool use_tma = true;             // tensor-map TMA pipeline kernel for the steps it covers (sbn_tma.h)
     bool chain_fits = true;          // false when a slot-arena operand of a segment needs > 32-bit byte offsets
     std::vector<int32_t> h_tile_words;  // host copy of d_tile_off
 };

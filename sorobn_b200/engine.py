@@ -189,7 +189,8 @@ class Program:
 
     def set_tiled(self, mode):
         """0: plain kernel; 1: tiled (default); 4: tiled, x-loop schedule only; 5: no slab variant;
-        7: on-chip segments on (csrc/sbn_chain.h, opt-in); 6: off again."""
+        7: on-chip segments on (csrc/sbn_chain.h, opt-in); 6: off again; 9: tensor-map TMA pipeline
+        kernel on for the steps it covers (csrc/sbn_tma.h, opt-in); 8: off again."""
         _check(load().sbn_program_set_tiled(self._h, int(mode)))
 
     def info(self) -> dict:

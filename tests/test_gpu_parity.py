@@ -723,3 +723,33 @@ def test_pipelined_host_path_equals_the_device_path():
     assert np.array_equal(host, again)
     small = prog.run(np.ascontiguousarray(codes[:, :1000]), 1000)  # below the threshold: single-stream path
     assert np.array_equal(small, host[:, :1000])
+
+
+@pytest.mark.parametrize("workload,rows", [("grid10x10", 5003), ("dag50", 2049)])
+def test_tensor_map_tma_kernel_matches_the_default_kernels(workload, rows):
+    """`sbn_step_tma` (csrc/sbn_tma.cu: the batched operands of a tile arrive as cp.async.bulk.tensor
+    boxes in a shared-memory ring, producer warp + four consumer warps, persistent CTAs) against the
+    register-preload kernels on the same program, at a ragged row count (the last row block's boxes
+    reach past `ld`: zero-filled by the tensor map), and against the oracle on a sample of rows."""
+    from oracle import ve_oracle
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.WORKLOADS[workload]()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    codes = wl.codes(bn, rows, seed=23)
+    prog = engine.Program(plan)
+    default = prog.run(codes, rows).copy()
+    prog.set_tiled(9)
+    tma = prog.run(codes, rows).copy()
+    assert np.array_equal(tma, prog.run(codes, rows))  # deterministic
+    assert np.allclose(tma, default, rtol=3e-6, atol=1e-30)
+    if workload == "grid10x10":
+        assert not np.array_equal(tma, default)  # the other kernel really ran (different rounding order)
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    order = [net.names[v] for v in plan.order]
+    for b in (0, rows // 3, rows - 1):
+        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        assert rel_err(tma[:, b], want) < RTOL, (b, tma[:, b], want)
