@@ -1531,23 +1531,29 @@ int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
     return SBN_OK;
 }
 
-int sbn_program_set_graph(sbn_program *P, int enabled) {
-    if (!P) return fail(SBN_E_INVALID, "null program");
-    P->use_graph = enabled != 0;
-    P->use_branches = enabled == 3;
+static void drop_graphs(sbn_program *P) {
+    // captured launches embed the kernel variants and pointers of the moment they were captured
     if (P->exec) {
         cudaGraphExecDestroy(P->exec);
         P->exec = nullptr;
     }
+    if (P->pipe_exec) {
+        cudaGraphExecDestroy(P->pipe_exec);
+        P->pipe_exec = nullptr;
+    }
+}
+
+int sbn_program_set_graph(sbn_program *P, int enabled) {
+    if (!P) return fail(SBN_E_INVALID, "null program");
+    P->use_graph = enabled != 0;
+    P->use_branches = enabled == 3;
+    drop_graphs(P);
     return SBN_OK;
 }
 
 int sbn_program_set_tiled(sbn_program *P, int enabled) {
     if (!P) return fail(SBN_E_INVALID, "null program");
-    if (P->exec) {
-        cudaGraphExecDestroy(P->exec);
-        P->exec = nullptr;
-    }
+    drop_graphs(P);
     P->use_tiled = enabled != 0;
     P->use_preload = enabled != 4;
     P->use_slab = enabled != 5;
