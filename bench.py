@@ -646,7 +646,8 @@ def run_b200(args, rank, world, local_rank):
             if rank == 0:
                 r2["steps"] = k
                 extra[name] = summarise_exact(r2, wl2)
-                extra[name]["scaling"] = "strong (1M rows over all GPUs)" if counts else "single GPU"
+                extra[name]["scaling"] = ("strong (1M rows over all GPUs)" if counts else
+                                          "weak (rows per GPU fixed)" if world > 1 else "single GPU")
         g = gibbs_extra(ctx, 3, 2)
         if rank == 0:
             extra["gibbs"] = g
