@@ -517,7 +517,7 @@ class BayesNet:
         batch with the batched float64 program; a row that is still NaN there is impossible."""
         n = codes.shape[1] if len(ev_vars) else len(bad)
         _, program = self._plan(query, ev_vars, _planner.MODE_BATCHED, device=device)
-        post = program.run(codes, n).astype(np.float64)  # [Q, n]
+        post = self._run_evicting(program, codes, n).astype(np.float64)  # [Q, n]
         suspect = np.isnan(post).any(axis=0) & ~bad
         rows = np.nonzero(suspect)[0]
         if len(rows) > 8:
@@ -528,6 +528,25 @@ class BayesNet:
             for b in rows:
                 post[:, b] = flat.run(np.ascontiguousarray(codes[:, b:b + 1]), 1)[:, 0]
         return post
+
+    def _run_evicting(self, program, codes, n):
+        """`program.run`, retried once after closing every OTHER cached device object when the device
+        is out of memory: each program owns a scratch arena sized for its largest batch (3.9 GB for
+        100k rows of the benchmark grid), and a BayesNet caches up to `max_cached_programs` of them --
+        many evidence patterns at large batches would otherwise exhaust the GPU long before the LRU
+        cap evicts anything."""
+        from . import engine
+
+        try:
+            return program.run(codes, n)
+        except engine.EngineError as exc:
+            if exc.code != engine.SBN_E_NOMEM:
+                raise
+        with self._cache_lock:
+            for key in [k for k, v in self._engine_cache.items() if (v[1] if isinstance(v, tuple) else v) is not program]:
+                old = self._engine_cache.pop(key)
+                (old[1] if isinstance(old, tuple) else old).close()
+        return program.run(codes, n)
 
     def _posterior_codes_multi(self, query, ev_vars, codes, bad, devices):
         """Row-shard `_posterior_codes` over several GPUs of this process: contiguous balanced

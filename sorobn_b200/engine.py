@@ -20,7 +20,14 @@ ABI_VERSION = 8
 
 
 class EngineError(RuntimeError):
-    pass
+    """An error reported by libsorobn_b200; `code` is the SBN_E_* value (-3 = device memory)."""
+
+    def __init__(self, message, code=None):
+        super().__init__(message)
+        self.code = code
+
+
+SBN_E_NOMEM = -3
 
 
 def lib_path() -> str:
@@ -104,7 +111,7 @@ EXPORTS = (
 
 def _check(rc: int):
     if rc != SBN_OK:
-        raise EngineError(f"libsorobn_b200 error {rc}: {load().sbn_last_error().decode(errors='replace')}")
+        raise EngineError(f"libsorobn_b200 error {rc}: {load().sbn_last_error().decode(errors='replace')}", code=rc)
 
 
 def device_count() -> int:

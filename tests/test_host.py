@@ -274,3 +274,38 @@ def test_chow_liu_matches_reference_edges():
     X = examples.sprinkler(seed=9).sample(4000)
     learned = BayesNet(*structure.chow_liu(X)).fit(X)
     assert learned.is_tree and learned._compiled is not None
+
+
+def test_out_of_memory_evicts_other_cached_programs_and_retries():
+    """A program whose scratch does not fit is retried once after every OTHER cached device object
+    has been closed (each owns an arena sized for its largest batch)."""
+    from sorobn_b200 import BayesNet, engine
+
+    class FakeProgram:
+        def __init__(self, fail_first):
+            self.fail_first, self.closed, self.calls = fail_first, False, 0
+
+        def run(self, codes, n):
+            self.calls += 1
+            if self.fail_first and self.calls == 1:
+                raise engine.EngineError("no memory", code=engine.SBN_E_NOMEM)
+            return np.zeros((2, n), dtype=np.float32)
+
+        def close(self):
+            self.closed = True
+
+    bn = BayesNet(("A", "B"))
+    mine, other, sampler = FakeProgram(True), FakeProgram(False), FakeProgram(False)
+    bn._engine_cache[("q1",)] = ("plan", mine)
+    bn._engine_cache[("q2",)] = ("plan", other)
+    bn._engine_cache[("sampler", "q3")] = sampler
+    out = bn._run_evicting(mine, np.zeros((1, 4), dtype=np.uint8), 4)
+    assert out.shape == (2, 4) and mine.calls == 2 and not mine.closed
+    assert other.closed and sampler.closed and list(bn._engine_cache) == [("q1",)]
+    # any other engine error is not swallowed
+    class Broken(FakeProgram):
+        def run(self, codes, n):
+            raise engine.EngineError("bad", code=-1)
+
+    with pytest.raises(engine.EngineError):
+        bn._run_evicting(Broken(False), np.zeros((1, 4), dtype=np.uint8), 4)
