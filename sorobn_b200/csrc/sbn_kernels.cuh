@@ -395,7 +395,7 @@ __device__ __forceinline__ void sbn_stv(float *ptr, const float (&r)[V]) {
 // A from shared memory and B blocks through registers (reloaded only when the block
 // changes).  Both factors are then read from HBM exactly once.
 template <int NU, int NA, int NB, int NC, int T, int V, int CX, bool SLAB = false, bool MX = false>
-__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && NU + NA + NB + NC <= 2) ? 3 : 2) : (NC > 0 ? 3 : 4)))
+__global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA + NB + NC <= 2 || CX <= 5)) ? 3 : 2) : (NC > 0 ? 3 : 4)))
     sbn_step_tiled(const __grid_constant__ SbnStep p) {
     constexpr int N_IN = NU + NA + NB + NC;
     constexpr int TB = (NB > 0 || NC > 0) ? T : 1;  // no input with axis 1: single-axis output
