@@ -19,6 +19,7 @@
 #include "sbn_gibbs.cuh"
 #include "sbn_internal.h"
 #include "sbn_kernels.cuh"
+#include "sbn_launch.h"
 #include "sbn_tma.h"
 
 namespace {
@@ -194,21 +195,8 @@ int parse(sbn_program *P, const int32_t *w, int64_t n) {
 }
 
 constexpr int kTiledMaxIn = 4;
-constexpr int kRowsPerThread = 2;
 constexpr int64_t kTileTableMax = 1 << 23;  // int32 words per step
 
-// CTA size of the regular tiled launches (the kernel reads blockDim.x); 128 unless overridden
-// for experiments
-int tiled_threads() {
-    static const int v = [] {
-        const char *e = getenv("SOROBN_B200_TILED_THREADS");
-        const int t = e ? atoi(e) : 0;
-        return (t == 32 || t == 64 || t == 128) ? t : SBN_TILED_THREADS;
-    }();
-    return v;
-}
-
-constexpr int kSlabThreads = 64;                 // CTA size of the slab variant (x kRowsPerThread rows)
 // Tables staged per CTA: SBN_SMEM_BUDGET keeps several CTAs per SM.  Opt-in experiment
 // (SOROBN_B200_SMEM_BIG=<KB>, up to 200): a launch around a larger CPT (8^5 entries = 128 KB) stages
 // it with ONE CTA per SM walking every tile of its rows.  Measured on dag50: no gain (4 warps per
@@ -222,7 +210,6 @@ int64_t smem_big() {
     }();
     return v;
 }
-constexpr int64_t kSlabSmemMax = 96 * 1024;      // bytes of shared memory one slab may take
 
 // Slab variant of the tiled kernel: eligible when the launch multiplies one batched factor on
 // the A side with one on the B side (plus at most one table without tile axes), both with
@@ -658,203 +645,25 @@ void build_params(const sbn_program *P, const StepDesc &st, const uint8_t *ev, i
     }
 }
 
-// Launch with the programmatic-dependent-launch attribute when enabled: the kernel may then be
-// scheduled while its predecessor on the stream is still draining; it calls
-// griddepcontrol.wait before touching anything a predecessor wrote (see sbn_pdl_wait).
-bool pdl_enabled() {
-    static const bool v = [] {
-        const char *e = getenv("SOROBN_B200_PDL");
-        return e ? atoi(e) != 0 : false;
-    }();
-    return v;
-}
-
-template <typename Kernel, typename... Args>
-void sbn_launch(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
-template <int N_IN>
-cudaError_t launch_batched_n(const SbnStep &q, int64_t grid, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
-    const dim3 g(static_cast<unsigned>(grid)), b(SBN_THREADS);
-#define SBN_CASE(CXV)                                                         \
-    case CXV:                                                                 \
-        sbn_launch(sbn_step_batched<N_IN, CXV>, g, b, smem, stream, q);               \
-        break;
-    if constexpr (N_IN <= 4) {
-        switch (q.cx) {
-            SBN_CASE(1)
-            SBN_CASE(2)
-            SBN_CASE(3)
-            SBN_CASE(4)
-            SBN_CASE(5)
-            SBN_CASE(6)
-            SBN_CASE(8)
-            default:
-                sbn_launch(sbn_step_batched<N_IN, 0>, g, b, smem, stream, q);
-        }
-    } else {
-        sbn_launch(sbn_step_batched<N_IN, 0>, g, b, smem, stream, q);
-    }
-#undef SBN_CASE
-    return cudaGetLastError();
-}
-
-template <int N_IN, int CX>
-cudaError_t set_smem_attr() {
-    return cudaFuncSetAttribute(sbn_step_batched<N_IN, CX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                SBN_SMEM_BUDGET);
-}
-template <int N_IN>
-cudaError_t set_smem_attr_n() {
-    cudaError_t e = set_smem_attr<N_IN, 0>();
-    if constexpr (N_IN <= 4) {
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 1>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 2>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 3>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 4>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 5>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 6>();
-        if (e == cudaSuccess) e = set_smem_attr<N_IN, 8>();
-    }
-    return e;
-}
-
-// (NU, NA, NB, NC) combinations instantiated.  Without a C-side input: NU <= 2, 1 <= NA <= 2,
-// NB <= 2, at most 4 inputs.  With one: NU, NA, NB <= 1.
-#define SBN_TILED_COMBOS(X)                                                                          \
-    X(0, 1, 0, 0) X(0, 1, 1, 0) X(0, 1, 2, 0) X(0, 2, 0, 0) X(0, 2, 1, 0) X(0, 2, 2, 0) X(1, 1, 0, 0)   \
-    X(1, 1, 1, 0) X(1, 1, 2, 0) X(1, 2, 0, 0) X(1, 2, 1, 0) X(2, 1, 0, 0) X(2, 1, 1, 0) X(2, 2, 0, 0)
-#define SBN_TILED_COMBOS_C(X)                                                                        \
-    X(0, 0, 0, 1) X(0, 0, 1, 1) X(0, 1, 0, 1) X(0, 1, 1, 1) X(1, 0, 0, 1) X(1, 0, 1, 1) X(1, 1, 0, 1)   \
-    X(1, 1, 1, 1)
-
-constexpr int kV = kRowsPerThread;  // evidence rows per thread of the tiled kernel
-
-// Preload variants (CX > 0) exist where the tile edge equals the eliminated cardinality
-// (networks with one cardinality throughout: 2, 3, 4, 5 states) and for 8 states (T = 4);
-// never with a C-side input or several eliminated variables.
-template <int NU, int NA, int NB, int NC>
-cudaError_t launch_tiled_c(const SbnStep &q, int tile, bool preload, int64_t grid, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(q.smem_floats) * 4;
-    const dim3 g(static_cast<unsigned>(grid)), b(tiled_threads());
-    if constexpr (NC > 0) {
-        switch (tile) {
-            case 2: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 2, kV, 0>, g, b, smem, stream, q); break;
-            case 3: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 3, kV, 0>, g, b, smem, stream, q); break;
-            case 4: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 4, kV, 0>, g, b, smem, stream, q); break;
-            case 5: sbn_launch(sbn_step_tiled<NU, NA, NB, NC, 5, kV, 0>, g, b, smem, stream, q); break;
-            default: return cudaErrorInvalidValue;
-        }
-    } else {
-#define SBN_T(TV)                                                                            \
-    case TV:                                                                                 \
-        if (preload && q.cx == TV && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV>, g, b, smem, stream, q); \
-        else if (preload && q.cx_inner == TV && q.zoff != nullptr)                                                  \
-            sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, TV, false, true>, g, b, smem, stream, q);                  \
-        else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, TV, kV, 0>, g, b, smem, stream, q);            \
-        break;
-        switch (tile) {
-            SBN_T(2)
-            SBN_T(3)
-            SBN_T(5)
-            case 4:
-                if (preload && q.cx == 4 && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4>, g, b, smem, stream, q);
-                else if (preload && q.cx == 8 && !q.zoff) sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8>, g, b, smem, stream, q);
-                else if (preload && q.cx_inner == 4 && q.zoff != nullptr)
-                    sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 4, false, true>, g, b, smem, stream, q);
-                else if (preload && q.cx_inner == 8 && q.zoff != nullptr)
-                    sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 8, false, true>, g, b, smem, stream, q);
-                else sbn_launch(sbn_step_tiled<NU, NA, NB, 0, 4, kV, 0>, g, b, smem, stream, q);
-                break;
-            default: return cudaErrorInvalidValue;
-        }
-#undef SBN_T
-    }
-    return cudaGetLastError();
-}
-
-template <int NU>
-cudaError_t launch_slab(const SbnStep &q, int tile, int64_t grid, cudaStream_t stream) {
-    const size_t smem = (static_cast<size_t>(q.slab_smem_off) + static_cast<size_t>(q.n_slab) * kSlabThreads * kV) * 4;
-    const dim3 g(static_cast<unsigned>(grid)), b(kSlabThreads);
-    switch (tile) {
-        case 2: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true>, g, b, smem, stream, q); break;
-        case 3: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true>, g, b, smem, stream, q); break;
-        case 5: sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true>, g, b, smem, stream, q); break;
-        case 4:
-            if (q.cx == 8) sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true>, g, b, smem, stream, q);
-            else sbn_launch(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true>, g, b, smem, stream, q);
-            break;
-        default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-}
-
-template <int NU>
-cudaError_t set_slab_attr() {
-    const int bytes = static_cast<int>(kSlabSmemMax) + SBN_SMEM_BUDGET;
-    cudaError_t e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 2, kV, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 3, kV, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 4, kV, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, 1, 1, 0, 5, kV, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    return e;
-}
-
 cudaError_t launch_tiled(const StepDesc &st, const SbnStep &q, bool preload, int64_t grid, cudaStream_t stream) {
-    if (q.slab_off != nullptr) return st.nu == 0 ? launch_slab<0>(q, st.tile, grid, stream) : launch_slab<1>(q, st.tile, grid, stream);
+    // the kernel instantiations live in four translation units (sbn_tiled_*.cu), grouped by the number of
+    // inputs without a tile axis / with a both-axes input
+    if (q.slab_off != nullptr) return sbn_slab_launch(st.nu, q, st.tile, grid, stream);
     const int key = st.nu * 1000 + st.na * 100 + st.nb * 10 + st.nc;
     // the preload schedule keeps every operand of a tile, for one block of eliminated states, in
     // registers: only for <= 3 inputs, or 4 when two of them carry no tile axis (one value per state)
     preload = preload && (st.in.size() <= 3 || (st.nu == 2 && st.na == 1 && st.nb == 1));
-    switch (key) {
-#define X(U, A, B, C) \
-    case U * 1000 + A * 100 + B * 10 + C: return launch_tiled_c<U, A, B, C>(q, st.tile, preload, grid, stream);
-        SBN_TILED_COMBOS(X)
-        SBN_TILED_COMBOS_C(X)
-#undef X
-    }
-    return cudaErrorInvalidValue;
+    if (st.nc > 0) return sbn_tiled_c_launch(key, q, st.tile, preload, grid, stream);
+    if (st.nu == 0) return sbn_tiled_u0_launch(key, q, st.tile, preload, grid, stream);
+    if (st.nu == 1) return sbn_tiled_u1_launch(key, q, st.tile, preload, grid, stream);
+    return sbn_tiled_u2_launch(key, q, st.tile, preload, grid, stream);
 }
 
-template <int NU, int NA, int NB, int NC>
-cudaError_t set_tiled_attr_c() {
-    cudaError_t e = cudaSuccess;
-#define SBN_A(TV, CXV) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, CXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
-    SBN_A(2, 0) SBN_A(3, 0) SBN_A(4, 0) SBN_A(5, 0)
-    if constexpr (NC == 0) {
-        SBN_A(2, 2) SBN_A(3, 3) SBN_A(4, 4) SBN_A(4, 8) SBN_A(5, 5)
-#define SBN_AM(TV) \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, TV, kV, TV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
-        SBN_AM(2) SBN_AM(3) SBN_AM(4) SBN_AM(5)
-#undef SBN_AM
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(sbn_step_tiled<NU, NA, NB, NC, 4, kV, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SBN_SMEM_BIG);
-    }
-#undef SBN_A
-    return e;
-}
 cudaError_t set_tiled_attrs() {
-    cudaError_t e = set_slab_attr<0>();
-    if (e == cudaSuccess) e = set_slab_attr<1>();
-#define X(U, A, B, C) \
-    if (e == cudaSuccess) e = set_tiled_attr_c<U, A, B, C>();
-    SBN_TILED_COMBOS(X)
-    SBN_TILED_COMBOS_C(X)
-#undef X
+    cudaError_t e = sbn_tiled_u0_set_attrs();
+    if (e == cudaSuccess) e = sbn_tiled_u1_set_attrs();
+    if (e == cudaSuccess) e = sbn_tiled_u2_set_attrs();
+    if (e == cudaSuccess) e = sbn_tiled_c_set_attrs();
     return e;
 }
 
@@ -893,17 +702,7 @@ cudaError_t launch_step(sbn_program *P, const StepDesc &st, const SbnStep &q, cu
         }
         return cudaGetLastError();
     }
-    switch (q.n_in) {
-        case 1: return launch_batched_n<1>(q, grid, stream);
-        case 2: return launch_batched_n<2>(q, grid, stream);
-        case 3: return launch_batched_n<3>(q, grid, stream);
-        case 4: return launch_batched_n<4>(q, grid, stream);
-        case 5: return launch_batched_n<5>(q, grid, stream);
-        case 6: return launch_batched_n<6>(q, grid, stream);
-        case 7: return launch_batched_n<7>(q, grid, stream);
-        case 8: return launch_batched_n<8>(q, grid, stream);
-    }
-    return cudaErrorInvalidValue;
+    return sbn_batched_launch(q, grid, stream);
 }
 
 cudaError_t launch_normalise(sbn_program *P, float *d_out, int64_t ld_out, int64_t n_rows, cudaStream_t stream) {
@@ -947,10 +746,31 @@ int run_table_steps(sbn_program *P) {
     return SBN_OK;
 }
 
+// The normalisation can ride in the posterior step when that step runs on the tiled kernel (not the
+// slab / TMA / plain variants) and its whole output is ONE tile (Q <= T x T joint query states).
+inline bool fold_normalise(const sbn_program *P, const StepDesc &st, const SbnStep &q) {
+#if !SBN_FOLD_NORMALISE
+    // Compiled out by default (sbn_kernels.cuh): measured on B200, the extra epilogue in every instantiation of
+    // the tiled kernel costs ~10 % on ALL launches (grid 3.14 -> 3.46 ms, dag50 7.26 -> 7.64 ms) to save one
+    // 6 us launch (Asia 30 -> 24 us).
+    (void)P;
+    (void)st;
+    (void)q;
+    return false;
+#endif
+    static const bool enabled = [] {
+        const char *e = getenv("SOROBN_B200_FOLD_NORMALISE");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return enabled && !P->f64 && P->post_batched && st.kind == 1 && q.tile_off != nullptr && q.slab_off == nullptr && st.n_tiles == 1 &&
+           st.n_out == P->Q && !sbn_tma_eligible(P, st);
+}
+
 int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows, float *d_out, int64_t ld_out,
               cudaStream_t stream, cudaEvent_t *events) {
     SbnStep q;
     int k = 0;
+    bool folded = false;
     for (const StepDesc &st : P->steps) {
         if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
         ++k;
@@ -963,10 +783,18 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
             continue;
         }
         build_params(P, st, d_ev, ld_ev, n_rows, &q);
+        if (k == static_cast<int>(P->steps.size()) && fold_normalise(P, st, q)) {
+            // the posterior step's whole output is one register tile: normalise there, skip the extra launch
+            q.norm_out = d_out;
+            q.norm_ld = ld_out;
+            q.norm_totals = P->d_total;
+            q.norm_min = SBN_MIN_TOTAL_F32;
+            folded = true;
+        }
         SBN_CUDA(launch_step(P, st, q, stream));
     }
     if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
-    if (!(chain_on(P) && !P->segments.empty() && P->segments.back()->ends_in_posterior))
+    if (!folded && !(chain_on(P) && !P->segments.empty() && P->segments.back()->ends_in_posterior))
         SBN_CUDA(launch_normalise(P, d_out, ld_out, n_rows, stream));
     if (events) SBN_CUDA(cudaEventRecord(events[k + 1], stream));
     return SBN_OK;
@@ -1164,14 +992,7 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
         // (once per device and process)
         static bool done[64] = {false};
         if (device < 64 && !done[device]) {
-            SBN_CUDA_P(set_smem_attr_n<1>());
-            SBN_CUDA_P(set_smem_attr_n<2>());
-            SBN_CUDA_P(set_smem_attr_n<3>());
-            SBN_CUDA_P(set_smem_attr_n<4>());
-            SBN_CUDA_P(set_smem_attr_n<5>());
-            SBN_CUDA_P(set_smem_attr_n<6>());
-            SBN_CUDA_P(set_smem_attr_n<7>());
-            SBN_CUDA_P(set_smem_attr_n<8>());
+            SBN_CUDA_P(sbn_batched_set_attrs());
             SBN_CUDA_P(set_tiled_attrs());
             SBN_CUDA_P(sbn_chain_set_attrs());
             SBN_CUDA_P(sbn_tma_set_attrs());

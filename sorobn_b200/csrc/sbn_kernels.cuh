@@ -24,6 +24,9 @@
 
 #include "../../include/sorobn_b200.h"
 
+#ifndef SBN_FOLD_NORMALISE
+#define SBN_FOLD_NORMALISE 0   // 1: normalisation inside the posterior step's epilogue (costs ~10 % on every tiled launch: off)
+#endif
 #define SBN_THREADS 128      // threads per CTA of the batched kernel (4 rows each)
 #define SBN_ROWS_PER_CTA (SBN_THREADS * 4)
 #define SBN_SMEM_BUDGET (64 * 1024)   // staged tables of an ordinary launch (several CTAs per SM)
@@ -70,6 +73,13 @@ struct SbnStep {
     int32_t slab_smem_off;            // float offset of the slab inside dynamic shared memory
     int32_t cx_inner;                 // states of the FIRST eliminated variable (block of the preload schedule)
     const int32_t *slices;            // sliced staging: [n_chunks][n_in][3] = first float, floats, smem offset
+    // fused normalisation (tiled kernel, the posterior step when its whole output is ONE tile): instead of
+    // storing the un-normalised tile, write posterior / total (range-checked like sbn_normalise) to norm_out
+    float *norm_out;                  // [Q][norm_ld], or nullptr
+    float *norm_totals;               // P(event) per row, or nullptr
+    int64_t norm_ld;
+    float norm_min;
+    int32_t pad_norm_;
     int32_t card[SBN_MAX_AXES];
     SbnInput in[SBN_MAX_IN];
 };
@@ -723,6 +733,44 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA 
                             }
                 }
             }
+#if SBN_FOLD_NORMALISE
+            if (p.norm_out != nullptr) {
+                // The tile IS the row's whole posterior: posterior / posterior.sum() (bayes_net.py:789-790)
+                // here, same summation order and range check as sbn_normalise (SBN_MIN_TOTAL_F32).
+                float total[V], lo[V];
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    total[l] = 0.f;
+                    lo[l] = p.norm_min;
+                }
+#pragma unroll
+                for (int d1 = 0; d1 < TB; ++d1)
+#pragma unroll
+                    for (int d0 = 0; d0 < T; ++d0)
+                        if (FULL || (d0 < na && d1 < nb)) {
+#pragma unroll
+                            for (int l = 0; l < V; ++l) {
+                                const float v = acc[d0][d1][l];
+                                total[l] += v;
+                                if (v > 0.f && v < lo[l]) lo[l] = v;
+                            }
+                        }
+                const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    if (b + l >= p.n_rows) continue;
+                    const bool ok = total[l] >= p.norm_min && lo[l] >= p.norm_min;  // false for NaN too
+                    if (p.norm_totals) p.norm_totals[b + l] = ok ? total[l] : nan;
+#pragma unroll
+                    for (int d1 = 0; d1 < TB; ++d1)
+#pragma unroll
+                        for (int d0 = 0; d0 < T; ++d0)
+                            if (FULL || (d0 < na && d1 < nb))
+                                p.norm_out[static_cast<int64_t>(o_base + d1 * c0 + d0) * p.norm_ld + b + l] = ok ? acc[d0][d1][l] / total[l] : nan;
+                }
+                return;
+            }
+#endif
 #pragma unroll
             for (int d1 = 0; d1 < TB; ++d1)
 #pragma unroll
