@@ -3,6 +3,12 @@
 Host-side (pandas / numpy), like the reference: mutual information of every pair of columns,
 maximum spanning tree over those weights, edges oriented away from a root.  The result feeds
 `BayesNet(*edges).fit(X)`, whose queries then run on the GPU.
+
+Off the hot path (kept from round 1; nothing here touches the device).  One deviation from the
+reference: its Kruskal loop stops as soon as every vertex has a neighbour (structure.py:33-41), so on
+some data it returns a FOREST; this one always completes the spanning tree.  On the reference's own
+example (tests/golden/chow_liu.json) the edge lists coincide; where they would not, this function has
+one extra edge per remaining component.
 """
 from __future__ import annotations
 
