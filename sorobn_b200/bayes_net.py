@@ -429,16 +429,39 @@ class BayesNet:
 
         ev_vars = tuple(event)
         plan, program = self._plan(query, ev_vars, _planner.MODE_FLAT)
-        codes, bad = self._encode_events(ev_vars, [[event[v]] for v in ev_vars])
-        index = self._answer_index(plan)
+        # One event is launch-latency bound on the device (~20 us): the host side must not cost ten
+        # times that.  State codes come from per-variable dicts, the answer's index is cached on the plan.
+        net = self._compiled
+        codes = np.empty((len(ev_vars), 1), dtype=np.uint8)
+        bad = False
+        for i, v in enumerate(ev_vars):
+            code = self._code_of(net.index[v]).get(event[v], -1)
+            bad |= code < 0
+            codes[i, 0] = max(code, 0)
+        index = getattr(plan, "_answer_index_cache", None)
+        if index is None:
+            index = plan._answer_index_cache = self._answer_index(plan)
         name = f"P({', '.join(map(str, query))})"
-        if bad.any():
+        if bad:  # a value outside the variable's domain: the reference's filter leaves nothing
             return pd.Series([], index=index[:0], name=name, dtype=np.float64)
         post = program.run(codes, 1)[:, 0].astype(np.float64)
-        answer = pd.Series(post, index=index, name=name)
         if np.isnan(post).any():  # impossible evidence: P(event) == 0
-            return answer.iloc[:0]
-        return answer[post > 0]
+            return pd.Series([], index=index[:0], name=name, dtype=np.float64)
+        keep = post > 0
+        if keep.all():
+            return pd.Series(post, index=index, name=name)
+        return pd.Series(post[keep], index=index[keep], name=name)
+
+    def _code_of(self, v):
+        """state value -> uint8 code of variable id `v` (position in its sorted domain)."""
+        cache = self.__dict__.setdefault("_code_cache", {})
+        table = cache.get(v)
+        if table is None or cache.get("net") is not self._compiled:
+            if cache.get("net") is not self._compiled:
+                cache.clear()
+                cache["net"] = self._compiled
+            table = cache[v] = {value: k for k, value in enumerate(self._compiled.domains[v])}
+        return table
 
     def _sample_query(self, algorithm, query, ev_vars, columns, n_rows, n_iterations):
         """The approximate algorithms on the device, per evidence row: one Gibbs chain

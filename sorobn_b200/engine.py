@@ -191,8 +191,10 @@ class Program:
     def reserve(self, max_rows: int):
         _check(load().sbn_program_reserve(self._h, int(max_rows)))
 
-    def set_graph(self, enabled: bool):
-        _check(load().sbn_program_set_graph(self._h, int(bool(enabled))))
+    def set_graph(self, mode):
+        """0 / False: plain launches; 1 / True: CUDA-graph replay (default); 3: graph with the independent
+        sub-trees of the elimination as parallel branches."""
+        _check(load().sbn_program_set_graph(self._h, int(mode)))
 
     def set_tiled(self, mode):
         """0: plain kernel; 1: tiled (default); 4: tiled, x-loop schedule only; 5: no slab variant;
