@@ -466,8 +466,9 @@ def exact_workload(ctx, wl, rows, steps, warmup, want_profile=False, counts=None
         sp.upload(codes_host.array[:n_ev])
         d_out = sp.d_out
         device_step = lambda: sp.run_resident(rows)  # noqa: E731
-        host_step = lambda: sp.run_host(codes_host.array[:n_ev], rows, counts=counts)  # noqa: E731
-        e2e_api = "sharding.ShardedProgram.run_host: pinned H2D, sbn_program_run_device, NCCL gather, D2H on rank 0"
+        host_step = lambda: sp.run_host(codes_host.array[:n_ev], rows, counts=counts, blocks=True)  # noqa: E731
+        e2e_api = ("sharding.ShardedProgram.run_host(blocks=True): pinned H2D, sbn_program_run_device, NCCL gather, "
+                   "D2H on rank 0 into per-rank [Q, rows] blocks")
     else:
         d_ev = torch.from_numpy(codes_host.array).to(dev)
         d_out = torch.empty((Q, rows), dtype=torch.float32, device=dev)

@@ -108,13 +108,15 @@ def _sharded_program_worker(rank, world, port, out_path):
         codes = prog.wl.codes(prog.bn, counts[rank], seed=100 + rank)  # every rank has its own rows
         for _ in range(2):  # buffers are reused between calls
             got = sp.run_host(codes, counts[rank], counts=counts)
+        parts = sp.run_host(codes, counts[rank], counts=counts, blocks=True)  # per-rank views, no host concatenation
         if rank == 0:
             want = np.concatenate([prog.run(prog.wl.codes(prog.bn, counts[r], seed=100 + r), counts[r])
                                    for r in range(world)], axis=1)
             assert got.shape == (2, sum(counts)) and np.array_equal(got, want)
+            assert [p.shape for p in parts] == [(2, c) for c in counts] and np.array_equal(np.concatenate(parts, axis=1), want)
             np.save(out_path, got)
         else:
-            assert got is None
+            assert got is None and parts is None
     finally:
         dist.destroy_process_group()
 
