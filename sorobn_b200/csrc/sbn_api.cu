@@ -1166,9 +1166,16 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
         return e ? atoi(e) : 1;
     }();
     if (pipe_env && !want_totals && n_rows <= cap && launches_per_run <= 8 && bytes >= (int64_t(2) << 20) && n_rows >= 4 * 32768) {
-        constexpr int kRanges = 4;
+        constexpr int kMaxRanges = 8;
+        static const int kRanges = [] {
+            const char *e = getenv("SOROBN_B200_PIPE_RANGES");
+            // swept on B200 (Asia, 1M rows, 4 MB in + 8 MB out): 2 / 3 / 4 / 6 / 8 ranges -> 0.240 / 0.235 / 0.245 /
+            // 0.251 / 0.253 ms, unpipelined 0.268 ms: the copies (51 GB/s for both directions together) are the bound
+            const int v = e ? atoi(e) : 3;
+            return v >= 2 && v <= kMaxRanges ? v : 3;
+        }();
         if (P->pipe_events.empty()) {
-            P->pipe_events.resize(3 + 2 * kRanges);
+            P->pipe_events.resize(3 + 2 * kMaxRanges);
             for (auto &e : P->pipe_events) SBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         cudaStream_t s_in = P->branch[0], s_run = P->stream, s_out = P->branch[1];
@@ -1228,7 +1235,7 @@ static int run_host_common(sbn_program *P, const uint8_t *ev, int64_t ld_ev, int
             P->use_graph = graph_was;
             if (as_graph) {
                 // join the side streams back into the origin, end the capture
-                cudaEvent_t j_in = P->pipe_events[1 + 2 * kRanges], j_out = P->pipe_events[2 + 2 * kRanges];
+                cudaEvent_t j_in = P->pipe_events[1 + 2 * kMaxRanges], j_out = P->pipe_events[2 + 2 * kMaxRanges];
                 if (e == cudaSuccess) e = cudaEventRecord(j_in, s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, j_in, 0);
                 if (e == cudaSuccess) e = cudaEventRecord(j_out, s_out);
