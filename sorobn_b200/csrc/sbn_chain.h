@@ -48,9 +48,9 @@ struct SbnChainIn {
     int32_t ev_card[SBN_MAX_EV];
 };
 
+// Host-side description of one step of a segment (sbn_chain_bind serialises it into the step
+// records the kernel reads from shared memory and into the producer's staging list).
 struct SbnChainStep {
-    const uint32_t *tiles;     // [n_tiles][2 + n_in]: out byte offset, na | nb << 8, input byte offsets
-    const uint32_t *xoff;      // [n_in][cx] byte offsets of the joint eliminated states, or nullptr (x * sxb)
     float *out_ptr;            // GLOBAL: slot base
     int32_t out_space;
     uint32_t out_off;          // bytes inside the arena / scratch
@@ -60,7 +60,7 @@ struct SbnChainStep {
     int32_t cx;                // joint states of the eliminated variables (1 = product only)
     int32_t n_in, n_tiles;
     int32_t table_bytes;       // bytes staged for this step (0 = none)
-    int32_t fast;              // 0 = generic step code, 1 = specialised shape, 2 = specialised with A0 in global memory
+    int32_t fast;              // 0 = generic step body; 1 + (A0 outside shared memory) + 2 * (B0 outside shared memory)
     SbnChainIn in[SBN_CHAIN_SLOTS];
 };
 
@@ -137,8 +137,7 @@ struct SbnSegment {
 };
 
 // After plan_tiles: partition the batched steps into segments (fills sbn_program::segments and
-// seg_first); a step outside every segment keeps its classic launch.  `tile_words` is the host
-// copy of d_tile_off (offsets only; device pointers are patched in sbn_chain_bind).
+// seg_first); a step outside every segment keeps its classic launch.
 void sbn_chain_plan(sbn_program *P);
 // After the slot arena exists (sbn_program_reserve): patch pointers, upload, size the scratch.
 cudaError_t sbn_chain_bind(sbn_program *P);
