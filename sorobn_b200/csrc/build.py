@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libsorobn_b200.so")
 SOURCES = [os.path.join(HERE, f) for f in ("sbn_api.cu", "sbn_tiled_u0.cu", "sbn_tiled_u1.cu", "sbn_tiled_u2.cu", "sbn_tiled_c.cu",
-                                            "sbn_chain.cu", "sbn_tma.cu")]
-HEADERS = [os.path.join(HERE, h) for h in ("sbn_kernels.cuh", "sbn_gibbs.cuh", "sbn_chain.h", "sbn_tma.h", "sbn_internal.h", "sbn_launch.h",
+                                            "sbn_chain.cu", "sbn_tma.cu", "sbn_pair.cu")]
+HEADERS = [os.path.join(HERE, h) for h in ("sbn_kernels.cuh", "sbn_gibbs.cuh", "sbn_chain.h", "sbn_tma.h", "sbn_pair.h", "sbn_internal.h", "sbn_launch.h",
                                             "sbn_launch_impl.cuh")] + [
     os.path.join(os.path.dirname(PKG), "include", "sorobn_b200.h")]
 OBJ_DIR = os.path.join(HERE, "build")

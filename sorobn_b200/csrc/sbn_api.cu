@@ -20,6 +20,7 @@
 #include "sbn_internal.h"
 #include "sbn_kernels.cuh"
 #include "sbn_launch.h"
+#include "sbn_pair.h"
 #include "sbn_tma.h"
 
 namespace {
@@ -730,6 +731,10 @@ inline bool chain_on(const sbn_program *P) {
     return P->use_chain && P->chain_fits && P->use_tiled && !P->use_branches && !P->segments.empty();
 }
 
+inline bool pair_on(const sbn_program *P) {
+    return P->use_pair && P->use_tiled && !P->use_branches && !chain_on(P) && !P->pairs.empty();
+}
+
 inline bool graph_allowed(const sbn_program *P) { return P->use_graph; }
 
 int run_table_steps(sbn_program *P) {
@@ -780,6 +785,13 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
         if (seg >= 0) {
             P->launches++;
             SBN_CUDA(sbn_chain_launch(P, *P->segments[seg], d_ev, ld_ev, n_rows, d_out, ld_out, stream));
+            continue;
+        }
+        const int pair = pair_on(P) ? P->pair_first[k - 1] : -1;
+        if (pair == -2) continue;      // computed by the launch of the step that feeds it
+        if (pair >= 0) {
+            P->launches++;
+            SBN_CUDA(sbn_pair_launch(P, *P->pairs[pair], d_ev, ld_ev, n_rows, stream));
             continue;
         }
         build_params(P, st, d_ev, ld_ev, n_rows, &q);
@@ -910,6 +922,8 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
         P->use_chain = e && atoi(e) != 0;  // on-chip segments are opt-in (see sbn_chain.cu)
         e = getenv("SOROBN_B200_TMA");
         P->use_tma = e && atoi(e) != 0;    // so is the tensor-map TMA pipeline kernel (see sbn_tma.cu: no gain measured)
+        e = getenv("SOROBN_B200_PAIR");
+        P->use_pair = e ? atoi(e) != 0 : true;  // paired steps (sbn_pair.h)
     }
     const size_t elem = f64 ? 8 : 4;
     int rc = parse(P, words, n_words);
@@ -1002,6 +1016,11 @@ static int create_common(int device, const int32_t *words, int64_t n_words, cons
 #undef SBN_CUDA_P
     rc = run_table_steps(P);
     if (rc != SBN_OK) return bail(rc);
+    {
+        // pairs multiply the tables of two steps on the host: needs the outputs of the table steps above
+        cudaError_t e = sbn_pair_plan(P);
+        if (e != cudaSuccess) return bail(fail(SBN_E_CUDA, "planning the paired steps failed: %s", cudaGetErrorString(e)));
+    }
     *out = P;
     return SBN_OK;
 }
@@ -1021,6 +1040,7 @@ void sbn_program_destroy(sbn_program *P) {
     cudaSetDevice(P->device);
     free_scratch(P);
     sbn_chain_free(P);
+    sbn_pair_free(P);
     cudaFree(P->d_shared);
     cudaFree(P->d_tile_off);
     cudaFree(P->d_tables);
@@ -1389,6 +1409,8 @@ int sbn_program_set_tiled(sbn_program *P, int enabled) {
     if (enabled == 9) P->use_tma = true;
     if (enabled == 6) P->use_chain = false;
     if (enabled == 7) P->use_chain = true;
+    if (enabled == 10) P->use_pair = false;
+    if (enabled == 11) P->use_pair = true;
     return SBN_OK;
 }
 

@@ -61,6 +61,7 @@ struct Slot {
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 struct SbnSegment;  // sbn_chain.h
+struct SbnPair;     // sbn_pair.h
 
 struct sbn_program {
     int device = 0;
@@ -122,5 +123,12 @@ struct sbn_program {
     bool use_tma = true;             // tensor-map TMA pipeline kernel for the steps it covers (sbn_tma.h)
     bool chain_fits = true;          // false when a slot-arena operand of a segment needs > 32-bit byte offsets
     std::vector<int32_t> h_tile_words;  // host copy of d_tile_off
+
+    // paired steps (sbn_pair.h): a step and its consumer as one launch, the intermediate in registers
+    std::vector<SbnPair *> pairs;
+    std::vector<int> pair_first;     // per step: >= 0 = first step of that pair, -2 = its second step, -1 = on its own
+    float *d_pair_canon = nullptr;   // canonical coefficient arrays of all pairs
+    int32_t *d_pair_tiles = nullptr; // their tile tables
+    bool use_pair = true;
 };
 

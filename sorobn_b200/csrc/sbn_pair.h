@@ -1,0 +1,89 @@
+// sorobn_b200 -- two eliminations in one launch ("paired steps").
+//
+// A run of `frontier <- sum_x table x frontier` steps (the benchmark grid's hot loop) writes every
+// 625-entry intermediate to HBM and reads it straight back: 5000 B per row and step.  When step k + 1
+// sums out a variable Y that the frontier F of step k already carries,
+//
+//     out[w, z, r] = sum_y c2[y, w, z, r] * ( sum_x c1[x, y, w, r] * F[x, y, r] )
+//
+// a thread that owns one row and one combination r of the untouched axes can keep the whole
+// intermediate mid[y, w] (T x T values) in registers: it loads the T x T entries F[., ., r], applies
+// step k, applies step k + 1 to the accumulators and stores the T x T entries out[., ., r].  The
+// intermediate never exists in memory: 5000 B per row for the pair instead of 10000.
+//
+//   x = the variable step k eliminates          y = the variable step k + 1 eliminates (an axis of F)
+//   w = a variable step k introduces            z = the variable step k + 1 introduces
+//
+// c1 / c2 are the products of the steps' tables (CPTs, hoisted table products).  They do not depend on
+// the batch, so they are multiplied together ONCE, when the program is created, into "canonical"
+// coefficient arrays laid out for the kernel (SbnPairMode below), zero-padded past the real
+// cardinalities: the kernel is one fixed T x T x T loop nest of FFMAs fed by shared-memory loads with
+// immediate offsets.  The arrays are staged in shared memory by one bulk-TMA copy per CTA.
+//
+// Reference operators fused by one launch: two rounds of `pointwise_mul` (bayes_net.py:253-256) +
+// `sum_out` (bayes_net.py:54-103), and the evidence filter of bayes_net.py:772-774.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/sorobn_b200.h"
+
+#define SBN_PAIR_T 5              // tile edge: every cardinality involved is <= 5
+#define SBN_PAIR_PW 8             // coefficients per innermost row (T padded to two float4)
+#define SBN_PAIR_MAX_EV 4         // evidence columns the tables of one step may gather
+#define SBN_PAIR_ROWS 256         // evidence rows per CTA
+#define SBN_PAIR_SMEM_MAX (40 * 1024)
+
+// evidence columns one canonical array is indexed by: float offset = sum_k min(code_k, card_k - 1) * stride_k
+struct SbnPairEv {
+    int32_t n;
+    int32_t col[SBN_PAIR_MAX_EV], stride[SBN_PAIR_MAX_EV], card[SBN_PAIR_MAX_EV];
+};
+
+struct SbnPairParams {
+    const float *f;               // the batched operand of the first step  [entries][ld]
+    float *out;                   // output of the second step               [entries][ld]
+    const uint8_t *ev;
+    const float *canon;           // canonical arrays of both steps (global; staged whole)
+    const int32_t *tile_off;      // [n_tiles][8] = out entry, F entry, float offsets of main 1, main 2, pre 1, pre 2, 0, 0
+    int64_t ld_ev, ld;
+    int32_t n_rows;
+    int32_t canon_floats;         // multiple of 4
+    int32_t n_tiles, tiles_per_cta, n_chunks;
+    int32_t f_sx, f_sy;           // entry strides of x and y in F
+    int32_t cx, cy, cw, cz;       // real cardinalities (<= T)
+    int32_t o_sw, o_sz;           // entry strides of w and z in the output
+    int32_t has_pre1, has_pre2;   // per-row factors applied to F[x][y] / mid[y][w] before the step's sum
+    SbnPairEv ev_main1, ev_main2, ev_pre1, ev_pre2;
+};
+
+// Layout of a step's main coefficient array (chosen per step when the program is created):
+//   B  -- no table carries the step's first tile axis: [evidence][r][x][8]        two float4 per x
+//   CU -- [x][d0][d1] coefficients, no evidence axis:  [r][x][d0][8]              two float4 per (x, d0), the same
+//                                                                                 address in every lane (broadcast)
+//   CE -- [x][d0][d1] coefficients per evidence row:   [evidence][r][x][d0][d1]   scalar loads; a slab is 125 floats,
+//                                                                                 odd, so the rows of a warp hit distinct banks
+// A table that has evidence axes but not the second tile axis is kept out of the main array when that
+// leaves the main array evidence-free: it becomes the "pre" factor [evidence][r][x][d0] applied to the
+// step's operand first (25 scalar loads) and the main coefficients stay a broadcast.
+enum SbnPairMode { SBN_PAIR_B = 0, SBN_PAIR_CU = 1, SBN_PAIR_CE = 2 };
+
+// One planned pair (host side).
+struct SbnPair {
+    int step1, step2;             // indices into sbn_program::steps
+    int f_in;                     // index of the batched operand among step1's inputs
+    int m1, m2;                   // SbnPairMode of the two steps
+    SbnPairParams q;              // everything but the run-time pointers
+    int64_t tile_off_pos;         // int32 offset into the pair tile table
+    int64_t canon_pos;            // float offset into the canonical coefficient buffer
+};
+
+struct sbn_program;
+// Called once, after the evidence-independent steps ran (their outputs are operands here).
+cudaError_t sbn_pair_plan(sbn_program *P);
+cudaError_t sbn_pair_launch(sbn_program *P, const SbnPair &pr, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows,
+                            cudaStream_t stream);
+cudaError_t sbn_pair_set_attrs();
+void sbn_pair_free(sbn_program *P);

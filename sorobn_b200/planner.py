@@ -648,14 +648,25 @@ def _assign_slots(steps, post_id, keep_unbatched=False):
         slots[best][2] = False
         return best
 
+    # The batched inputs of a batched step are released one batched step LATE: the engine may run a
+    # step and its consumer as ONE launch that reads the first step's operand and writes the second
+    # step's output (csrc/sbn_pair.h), so those two must never share a buffer.
+    parked = []
     for st in steps:
         size = int(np.prod(st.cards, dtype=np.int64)) if st.cards else 1
         st.out_slot = alloc(st.kind == KIND_BATCHED, size)
+        if st.kind == KIND_BATCHED:
+            for phys in parked:
+                slots[phys][2] = True
+            parked = []
         new_inputs = []
         for f, es, ss in st.inputs:
             if f.is_slot:
                 phys = where.pop(f.buf)
-                slots[phys][2] = not (keep_unbatched and not slots[phys][0])
+                if slots[phys][0] and st.kind == KIND_BATCHED:
+                    parked.append(phys)
+                else:
+                    slots[phys][2] = not (keep_unbatched and not slots[phys][0])
                 f = _Factor(True, phys, f.vars, f.strides, f.ev, f.batched)
             new_inputs.append((f, es, ss))
         st.inputs = new_inputs

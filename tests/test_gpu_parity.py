@@ -753,3 +753,48 @@ def test_tensor_map_tma_kernel_matches_the_default_kernels(workload, rows):
         ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
         want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
         assert rel_err(tma[:, b], want) < RTOL, (b, tma[:, b], want)
+
+
+@pytest.mark.parametrize("workload,rows", [("grid10x10", 5003), ("grid10x10", 257), ("dag50", 2049), ("asia_1m", 3001)])
+def test_paired_steps_match_single_step_launches_and_the_oracle(workload, rows):
+    """`sbn_pair_kernel` (csrc/sbn_pair.cu: a step and its consumer as ONE launch, the intermediate
+    factor in registers, the tables of both steps pre-multiplied into canonical coefficient arrays)
+    against one launch per step on the same program, at a ragged row count, and against the oracle
+    on a sample of rows."""
+    from oracle import ve_oracle
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.WORKLOADS[workload]()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    codes = wl.codes(bn, rows, seed=29)
+    prog = engine.Program(plan)
+    prog.set_graph(False)
+
+    def run():
+        before = prog.info()["launches"]
+        out = prog.run(codes, rows).copy()
+        return out, prog.info()["launches"] - before
+
+    paired, n_paired = run()
+    assert np.array_equal(paired, run()[0])  # deterministic
+    prog.set_tiled(10)
+    single, n_single = run()
+    prog.set_tiled(11)
+    assert np.isfinite(single).all()
+    assert np.allclose(paired, single, rtol=3e-6, atol=1e-30)
+    if workload == "grid10x10":
+        assert n_single - n_paired >= 7, (n_single, n_paired)  # the frontier chains of the grid pair up
+        assert not np.array_equal(paired, single)
+    prog.set_graph(True)
+    assert np.array_equal(prog.run(codes, rows), paired)  # the captured graph replays the same launches
+    dn = ve_oracle.dense_from_pandas(bn.P, bn.parents, bn.nodes)
+    order = [net.names[v] for v in plan.order]
+    for b in sorted({0, rows // 3, rows // 2, rows - 1}):
+        ev = {v: net.domains[net.index[v]][codes[i, b]] for i, v in enumerate(wl.evidence)}
+        want = ve_oracle.query(dn, *wl.query, event=ev, order=order)[1].reshape(-1)
+        assert rel_err(paired[:, b], want) < RTOL, (b, paired[:, b], want)
+    p_pair = prog.evidence(codes, rows)
+    prog.set_tiled(10)
+    assert np.allclose(p_pair, prog.evidence(codes, rows), rtol=3e-6, atol=0)
