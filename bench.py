@@ -503,8 +503,10 @@ def exact_workload(ctx, wl, rows, steps, warmup, want_profile=False, counts=None
         "e2e_ms_per_step": 1e3 * e2e_s / steps, "e2e_value": total_rows / (e2e_s / steps),
         "h2d": int(n_ev * rows) * world, "d2h": int(Q * rows * 4) * world, "e2e_api": e2e_api,
         "launches": int(launches) * world, "ok": ok, "same": same, "total_rows": total_rows,
-        "whole_step_frac": (plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9) / measured_peak()[0],
+        # bytes the launches as issued move: paired steps keep their intermediate in registers
+        "bytes_issued_per_row": plan.bytes_per_row() - prog.info()["pair_bytes_saved_per_row"],
     }
+    res["whole_step_frac"] = (res["bytes_issued_per_row"] * rows / (ms_per_step * 1e-3) / 1e9) / measured_peak()[0]
     if want_profile and not distributed:
         d_ev_ptr = d_ev.data_ptr()
         prof = None
@@ -523,7 +525,8 @@ def summarise_exact(res, wl):
         "value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"],
         "e2e": {"value": res["e2e_value"], "unit": UNIT, "ms_per_step": res["e2e_ms_per_step"],
                 "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"], "api": res["e2e_api"]},
-        "algorithmic_bytes_per_row": plan.bytes_per_row(), "hbm_roofline_frac_whole_step": res["whole_step_frac"],
+        "algorithmic_bytes_per_row": plan.bytes_per_row(), "bytes_per_row_as_issued": res["bytes_issued_per_row"],
+        "hbm_roofline_frac_whole_step": res["whole_step_frac"],
         "launches_per_step": res["launches"] // max(1, res.get("steps", 1)),
         "l2": "flushed (256 MB write) between timed steps" if res["flush"] else "not flushed (step streams >> 126 MB)",
         "checks": {"posteriors_sum_to_one": res["ok"], "host_path_equals_device_path": res["same"]},
@@ -669,14 +672,20 @@ def run_b200(args, rank, world, local_rank):
             kern = float(sum(ms for ms, st in zip(prof[:-1], plan.steps) if st.kind == planner.KIND_BATCHED))
             share = kern / float(prof.sum()) if prof.sum() > 0 else 1.0
             kernel_ms = ms_per_step * share
-            kernel_bytes = float(sum(sb)) * rows
+            # paired steps (csrc/sbn_pair.h) keep their intermediate in registers: those bytes are not moved
+            # and do not count -- the figure is what the launches as issued have to read and write
+            info = prog.info()
+            kernel_bytes = float(sum(sb) - info["pair_bytes_saved_per_row"]) * rows
             achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
             traffic = ncu_traffic(wl.name) if rows == wl.default_rows else None
+            n_batched = int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED))
             roofline.update({
-                "kernel": "sbn_step_tiled (every batched step of the program)", "achieved": achieved, "frac": achieved / peak,
+                "kernel": "sbn_step_tiled + sbn_pair_kernel (every batched step of the program)", "achieved": achieved,
+                "frac": achieved / peak,
                 "algorithmic_bytes_per_step": kernel_bytes, "kernel_ms_per_step": kernel_ms,
                 "kernel_share_of_step": share,
-                "launches_per_step": int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED)),
+                "launches_per_step": n_batched - info["pairs"], "paired_launches": info["pairs"],
+                "bytes_per_row_one_launch_per_step": int(sum(sb)), "bytes_per_row_as_issued": int(sum(sb) - info["pair_bytes_saved_per_row"]),
                 "traffic": (traffic or {}).get("dram_bytes_per_step"), "traffic_detail": traffic,
             })
             if args.dump:
@@ -688,7 +697,7 @@ def run_b200(args, rank, world, local_rank):
                                                      + (f"e{len(fct.ev)}" if fct.ev else "") for fct, _, _ in st.inputs]}
                                          for st in plan.steps]}, f)
         else:
-            achieved = plan.bytes_per_row() * rows / (ms_per_step * 1e-3) / 1e9
+            achieved = res["bytes_issued_per_row"] * rows / (ms_per_step * 1e-3) / 1e9
             roofline.update({"kernel": "whole step (per-launch profile only at N = 1)", "achieved": achieved,
                              "frac": achieved / peak, "traffic": None})
 
@@ -711,7 +720,7 @@ def run_b200(args, rank, world, local_rank):
             "plan": {
                 "parallelism": f"rows sharded x{world}; NCCL gather of posteriors",
                 "elimination_steps": len(plan.steps), "max_factor_entries_per_row": plan.max_factor_per_row(),
-                "algorithmic_bytes_per_row": plan.bytes_per_row(),
+                "algorithmic_bytes_per_row": plan.bytes_per_row(), "bytes_per_row_as_issued": res["bytes_issued_per_row"],
                 "l2": ("flushed (256 MB write) between timed steps" if res["flush"] else
                        f"not flushed: each step streams {plan.bytes_per_row() * rows / 1e9:.2f} GB of factors >> 126 MB L2"),
             },

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SBN_ABI_VERSION 8
+#define SBN_ABI_VERSION 9
 
 #define SBN_OK 0
 #define SBN_E_INVALID (-1)   /* malformed program / bad argument            */
@@ -114,7 +114,9 @@ int sbn_program_profile(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, i
  * [5]=kernel launches issued by this program so far  [6]=mode (0 flat, 1 batched)
  * [7]=unbatched scratch floats
  * with n_info >= 12 also: [8]=on-chip segments in use  [9]=steps they cover  [10]=bytes per row the
- * segments still move through the HBM slot arena  [11]=per-CTA private scratch floats */
+ * segments still move through the HBM slot arena  [11]=per-CTA private scratch floats
+ * with n_info >= 14 also: [12]=paired launches in use (a step and its consumer as one kernel, csrc/sbn_pair.h)
+ * [13]=bytes per row those pairs do not move (their intermediates stay in registers) */
 int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 
 /* 0 = plain launches; 1 = CUDA-graph replay of the step sequence (default); 3 = graph replay
@@ -130,7 +132,10 @@ int sbn_program_set_graph(sbn_program *prog, int enabled);
  * shared memory / an L2-resident scratch; opt-in, also SOROBN_B200_CHAIN=1), 6 = back to one launch
  * per step; 9 = run the steps it covers through the tensor-map TMA pipeline kernel (csrc/sbn_tma.h: 2-D / 4-D
  * `cp.async.bulk.tensor` boxes into a shared-memory ring fed by a producer warp; opt-in, also SOROBN_B200_TMA=1:
- * parity-green but not faster than the register-preload kernel), 8 = off again. */
+ * parity-green but not faster than the register-preload kernel), 8 = off again;
+ * 10 = no paired steps (every step its own launch), 11 = paired steps where eligible (default; csrc/sbn_pair.h:
+ * a step and its consumer run as ONE kernel that keeps the intermediate factor in registers; SOROBN_B200_PAIR=0
+ * disables them at creation). */
 int sbn_program_set_tiled(sbn_program *prog, int enabled);
 
 /* ------------------------------------------------------------------ Gibbs sampling

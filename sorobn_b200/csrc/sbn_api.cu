@@ -1365,6 +1365,12 @@ int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
         info[10] = chain_on(P) ? hbm : 0;
         info[11] = scratch;
     }
+    if (n_info >= 14) {
+        int64_t saved = 0;
+        for (const SbnPair *pr : P->pairs) saved += 8 * P->steps[pr->step1].n_out;  // one fp32 write + one read per entry
+        info[12] = pair_on(P) ? static_cast<int64_t>(P->pairs.size()) : 0;
+        info[13] = pair_on(P) ? saved : 0;
+    }
     info[0] = P->Q;
     info[1] = P->n_ev;
     info[2] = static_cast<int64_t>(P->steps.size());

@@ -76,8 +76,10 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
 //   step 2: out[w][z] = sum_y c2[y][w][z] * pre2[y][w] * mid[y][w]
 // Coefficients past a real cardinality are zero, F indices past one are clamped: the loop nest is
 // always T x T x T and only the stores are predicated.
+// Five CTAs per SM (96 registers, a handful of spilled bytes): measured on B200, grid 100k rows, 2 / 3 / 4 / 5 / 6 / 8
+// resident CTAs -> 2.65 / 2.65 / 2.57 / 2.52 / 2.60 / 2.92 ms per step.
 template <int M1, int M2>
-__global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 3) sbn_pair_kernel(const __grid_constant__ SbnPairParams p) {
+__global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const __grid_constant__ SbnPairParams p) {
     constexpr int T = SBN_PAIR_T, V = kV;
     extern __shared__ __align__(16) float s_canon[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -163,9 +165,9 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 3) sbn_pair_kernel(const _
 
 void launch_modes(const SbnPair &pr, const SbnPairParams &q, unsigned grid, size_t smem, cudaStream_t stream) {
     const dim3 g(grid), b(SBN_PAIR_ROWS / kV);
-#define SBN_PAIR_CASE(A, B)                                                        \
-    case A * 3 + B:                                                                \
-        sbn_launch(sbn_pair_kernel<A, B>, g, b, smem, stream, q);                  \
+#define SBN_PAIR_CASE(A, B)                                          \
+    case A * 3 + B:                                                  \
+        sbn_launch(sbn_pair_kernel<A, B>, g, b, smem, stream, q);    \
         break;
     switch (pr.m1 * 3 + pr.m2) {
         SBN_PAIR_CASE(0, 0)

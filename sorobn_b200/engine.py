@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsorobn_
 _lib = None
 
 SBN_OK = 0
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class EngineError(RuntimeError):
@@ -199,15 +199,16 @@ class Program:
     def set_tiled(self, mode):
         """0: plain kernel; 1: tiled (default); 4: tiled, x-loop schedule only; 5: no slab variant;
         7: on-chip segments on (csrc/sbn_chain.h, opt-in); 6: off again; 9: tensor-map TMA pipeline
-        kernel on for the steps it covers (csrc/sbn_tma.h, opt-in); 8: off again."""
+        kernel on for the steps it covers (csrc/sbn_tma.h, opt-in); 8: off again; 10: no paired steps; 11: paired
+        steps where eligible (default; csrc/sbn_pair.h)."""
         _check(load().sbn_program_set_tiled(self._h, int(mode)))
 
     def info(self) -> dict:
-        buf = (ctypes.c_int64 * 12)()
-        _check(load().sbn_program_info(self._h, buf, 12))
+        buf = (ctypes.c_int64 * 14)()
+        _check(load().sbn_program_info(self._h, buf, 14))
         keys = ("Q", "n_ev", "n_steps", "scratch_floats_per_row", "reserved_rows", "launches", "mode",
                 "shared_scratch_floats", "segments", "segment_steps", "segment_hbm_bytes_per_row",
-                "segment_scratch_floats")
+                "segment_scratch_floats", "pairs", "pair_bytes_saved_per_row")
         return dict(zip(keys, [int(x) for x in buf]))
 
     # --------------------------------------------------------------------- runs

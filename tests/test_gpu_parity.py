@@ -388,6 +388,7 @@ def test_graph_branches_match_linear_replay_and_plain_launches():
         net = bn._compiled
         plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
         prog = engine.Program(plan)
+        prog.set_tiled(10)  # the branched capture issues one launch per step: compare like with like (no paired steps)
         codes = wl.codes(bn, B, seed=21)
         prog.set_graph(0)
         want = prog.run(codes, B).copy()
@@ -784,6 +785,7 @@ def test_paired_steps_match_single_step_launches_and_the_oracle(workload, rows):
     prog.set_tiled(11)
     assert np.isfinite(single).all()
     assert np.allclose(paired, single, rtol=3e-6, atol=1e-30)
+    assert prog.info()["pairs"] == n_single - n_paired and prog.info()["pair_bytes_saved_per_row"] >= 8 * prog.info()["pairs"]
     if workload == "grid10x10":
         assert n_single - n_paired >= 7, (n_single, n_paired)  # the frontier chains of the grid pair up
         assert not np.array_equal(paired, single)

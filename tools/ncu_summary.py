@@ -34,7 +34,7 @@ step = [l for l in launches if "sbn_" in l["kernel"]]
 total_us = sum(l["us"] for l in step)
 by_kernel = {}
 for l in step:
-    fam = l["kernel"].split("<")[0].replace("void ", "")
+    fam = l["kernel"].replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("<")[0]
     d = by_kernel.setdefault(fam, {"launches": 0, "us": 0.0, "dram_bytes": 0.0})
     d["launches"] += 1
     d["us"] += l["us"]
@@ -60,7 +60,7 @@ traffic = {}
 if os.path.exists(traffic_path):
     traffic = json.load(open(traffic_path))
 dom = max(by_kernel.items(), key=lambda kv: kv[1]["us"])
-steps_only = {k: v for k, v in by_kernel.items() if k.startswith("sbn_step")}
+steps_only = {k: v for k, v in by_kernel.items() if k.startswith("sbn_step") or k.startswith("sbn_pair")}
 traffic[workload] = {
     "dram_bytes_per_step": sum(v["dram_bytes"] for v in steps_only.values()),
     "launches_per_step": sum(v["launches"] for v in steps_only.values()),
