@@ -679,14 +679,52 @@ def run_b200(args, rank, world, local_rank):
             achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
             traffic = ncu_traffic(wl.name) if rows == wl.default_rows else None
             n_batched = int(sum(1 for st in plan.steps if st.kind == planner.KIND_BATCHED))
+            # per kernel family: bytes its launches move / their share of the timed step (roles from the engine)
+            roles = prog.step_roles()
+            fam_of = {1: "sbn_step_tiled", 2: "sbn_pair_kernel", 3: "sbn_pair_kernel", 4: "sbn_triple_kernel", 5: "sbn_triple_kernel"}
+            fams = {}
+            mid = 0  # bytes per row of the intermediate a fused launch keeps on chip
+            for i, st in enumerate(plan.steps):
+                role = int(roles[i])
+                fam = fam_of.get(role)
+                if fam is None:
+                    continue
+                d = fams.setdefault(fam, {"launches": 0, "bytes_per_row": 0, "ms": 0.0})
+                d["ms"] += float(prof[i])
+                if role in (2, 4):    # first step of a fused launch: its output is never written ...
+                    mid = 4 * int(np.prod(st.cards, dtype=np.int64))
+                    d["bytes_per_row"] += sb[i] - mid
+                elif role in (3, 5):  # ... nor read back by the second
+                    d["bytes_per_row"] += sb[i] - mid
+                else:
+                    d["bytes_per_row"] += sb[i]
+                d["launches"] += 1 if role in (1, 2, 4) else 0
+            for d in fams.values():
+                d["ms"] *= ms_per_step / float(prof.sum())
+                d["achieved_gbs"] = d["bytes_per_row"] * rows / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else None
+                d["frac"] = d["achieved_gbs"] / peak if d["ms"] > 0 else None
+                d["share_of_step"] = d["ms"] / ms_per_step
+            # headline = the dominant kernel family, per launch; the aggregate over every step kernel beside it
+            dom_name, dom = max(fams.items(), key=lambda kv: kv[1]["ms"])
+            dom_traffic = None
+            if traffic and traffic.get("by_kernel", {}).get(dom_name):
+                tk = traffic["by_kernel"][dom_name]
+                dom_traffic = tk["dram_bytes"] / max(1, tk["launches"])
             roofline.update({
-                "kernel": "sbn_step_tiled + sbn_pair_kernel (every batched step of the program)", "achieved": achieved,
-                "frac": achieved / peak,
-                "algorithmic_bytes_per_step": kernel_bytes, "kernel_ms_per_step": kernel_ms,
-                "kernel_share_of_step": share,
-                "launches_per_step": n_batched - info["pairs"], "paired_launches": info["pairs"],
-                "bytes_per_row_one_launch_per_step": int(sum(sb)), "bytes_per_row_as_issued": int(sum(sb) - info["pair_bytes_saved_per_row"]),
-                "traffic": (traffic or {}).get("dram_bytes_per_step"), "traffic_detail": traffic,
+                "kernel": f"{dom_name} ({dom['launches']} launches per step, {dom['share_of_step']:.0%} of the step)",
+                "achieved": dom["achieved_gbs"], "frac": dom["frac"],
+                "algorithmic_bytes_per_launch": dom["bytes_per_row"] * rows / max(1, dom["launches"]),
+                "avg_launch_ms": dom["ms"] / max(1, dom["launches"]),
+                "traffic": dom_traffic,
+                "all_step_kernels": {
+                    "achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_step": kernel_bytes,
+                    "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": share,
+                    "launches_per_step": n_batched - info["pairs"], "fused_launches": info["pairs"],
+                    "bytes_per_row_one_launch_per_step": int(sum(sb)),
+                    "bytes_per_row_as_issued": int(sum(sb) - info["pair_bytes_saved_per_row"]),
+                    "traffic": (traffic or {}).get("dram_bytes_per_step"),
+                },
+                "by_kernel": fams, "traffic_detail": traffic,
             })
             if args.dump:
                 with open(args.dump, "w") as f:

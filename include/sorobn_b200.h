@@ -119,6 +119,12 @@ int sbn_program_profile(sbn_program *prog, const uint8_t *d_ev, int64_t ld_ev, i
  * [13]=bytes per row those pairs do not move (their intermediates stay in registers) */
 int sbn_program_info(const sbn_program *prog, int64_t *info, int64_t n_info);
 
+/* How every program step is executed with the current switches: roles[i] = 0 evidence-independent (ran once, at
+ * creation; or any step of a flat program), 1 its own launch, 2 / 3 first / second step of a paired launch
+ * (csrc/sbn_pair.h: table x frontier twice), 4 / 5 first / second step of an expanding product fused with its
+ * consumer, 6 inside an on-chip segment.  n_roles >= n_steps. */
+int sbn_program_step_roles(const sbn_program *prog, int32_t *roles, int64_t n_roles);
+
 /* 0 = plain launches; 1 = CUDA-graph replay of the step sequence (default); 3 = graph replay
  * with independent sub-trees of the elimination as parallel branches (experimental: measured
  * no gain on the benchmark plans, which are one long dependency chain). */

@@ -776,6 +776,7 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
     SbnStep q;
     int k = 0;
     bool folded = false;
+    bool skip_second = false;  // the pair launched last covers the next launched step
     for (const StepDesc &st : P->steps) {
         if (events) SBN_CUDA(cudaEventRecord(events[k], stream));
         ++k;
@@ -787,9 +788,13 @@ int issue_all(sbn_program *P, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows
             SBN_CUDA(sbn_chain_launch(P, *P->segments[seg], d_ev, ld_ev, n_rows, d_out, ld_out, stream));
             continue;
         }
-        const int pair = pair_on(P) ? P->pair_first[k - 1] : -1;
+        int pair = pair_on(P) ? P->pair_first[k - 1] : -1;
+        if (pair == -2 && !skip_second) pair = -1;  // its first step ran on its own (row pitch beyond 32-bit offsets)
+        skip_second = false;
         if (pair == -2) continue;      // computed by the launch of the step that feeds it
+        if (pair >= 0 && !sbn_pair_fits(P, *P->pairs[pair])) pair = -1;
         if (pair >= 0) {
+            skip_second = true;
             P->launches++;
             SBN_CUDA(sbn_pair_launch(P, *P->pairs[pair], d_ev, ld_ev, n_rows, stream));
             continue;
@@ -1382,6 +1387,34 @@ int sbn_program_info(const sbn_program *P, int64_t *info, int64_t n_info) {
     for (const Slot &s : P->slots)
         if (!s.batched) shared += s.size;
     info[7] = shared;
+    return SBN_OK;
+}
+
+int sbn_program_step_roles(const sbn_program *P, int32_t *roles, int64_t n_roles) {
+    if (!P || !roles || n_roles < static_cast<int64_t>(P->steps.size())) return fail(SBN_E_INVALID, "roles needs n_steps entries");
+    int first_kind = 0;
+    bool second_follows = false;
+    for (size_t i = 0; i < P->steps.size(); ++i) {
+        const StepDesc &st = P->steps[i];
+        if (P->mode != 1 || hoisted(P, st)) {
+            roles[i] = 0;
+            continue;
+        }
+        roles[i] = 1;
+        if (chain_on(P) && P->seg_first[i] != -1) {
+            roles[i] = 6;
+            continue;
+        }
+        int pair = pair_on(P) ? P->pair_first[i] : -1;
+        if (pair == -2 && !second_follows) pair = -1;
+        second_follows = false;
+        if (pair == -2) roles[i] = first_kind == 1 ? 5 : 3;
+        if (pair >= 0 && sbn_pair_fits(P, *P->pairs[pair])) {
+            first_kind = P->pairs[pair]->kind;
+            roles[i] = first_kind == 1 ? 4 : 2;
+            second_follows = true;
+        }
+    }
     return SBN_OK;
 }
 

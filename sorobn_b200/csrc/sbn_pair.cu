@@ -109,14 +109,18 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
     sbn_mbar_wait(&s_bar, 0);
     if (!live) return;
 
-    const int64_t ld = p.ld;
+    // element offsets fit 32 bits (sbn_pair_fits): strides are scaled by the row pitch once, an access then costs
+    // one IADD3 and one IMAD.WIDE.U32
+    const uint32_t ld = static_cast<uint32_t>(p.ld);
     const float *const fp = p.f + b;
     float *const op = p.out + b;
-    int xs[T], ys[T];
+    uint32_t xs[T], ys[T], ow[T], oz[T];
 #pragma unroll
     for (int d = 0; d < T; ++d) {
-        xs[d] = min(d, p.cx - 1) * p.f_sx;
-        ys[d] = min(d, p.cy - 1) * p.f_sy;
+        xs[d] = static_cast<uint32_t>(min(d, p.cx - 1) * p.f_sx) * ld;
+        ys[d] = static_cast<uint32_t>(min(d, p.cy - 1) * p.f_sy) * ld;
+        ow[d] = static_cast<uint32_t>(d * p.o_sw) * ld;
+        oz[d] = static_cast<uint32_t>(d * p.o_sz) * ld;
     }
     const int t_begin = chunk * p.tiles_per_cta;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
@@ -124,14 +128,14 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
     for (int t = t_begin; t < t_end; ++t) {
         const int4 r0 = __ldg(reinterpret_cast<const int4 *>(p.tile_off) + 2 * t);
         const int4 r1 = __ldg(reinterpret_cast<const int4 *>(p.tile_off) + 2 * t + 1);
-        const int ob = r0.x, fb = r0.y;
+        const uint32_t ob = static_cast<uint32_t>(r0.x) * ld, fb = static_cast<uint32_t>(r0.y) * ld;
 
         // every entry of F this tile needs, in flight together
         float f[T][T][V];
 #pragma unroll
         for (int x = 0; x < T; ++x)
 #pragma unroll
-            for (int y = 0; y < T; ++y) sbn_ldv<V>(f[x][y], fp + static_cast<int64_t>(fb + xs[x] + ys[y]) * ld);
+            for (int y = 0; y < T; ++y) sbn_ldv<V>(f[x][y], fp + (fb + xs[x] + ys[y]));
         if (p.has_pre1) {
             const float *const k = s_canon + r1.x;
 #pragma unroll
@@ -159,7 +163,83 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
         for (int z = 0; z < T; ++z)
 #pragma unroll
             for (int w = 0; w < T; ++w)
-                if (w < p.cw && z < p.cz) sbn_stv<V>(op + static_cast<int64_t>(ob + w * p.o_sw + z * p.o_sz) * ld, acc[w][z]);
+                if (w < p.cw && z < p.cz) sbn_stv<V>(op + (ob + ow[w] + oz[z]), acc[w][z]);
+    }
+}
+
+// Expanding product + contraction (SbnTripleParams): thread = one evidence row x one combination of the untouched axes.
+// threadIdx.y walks the digits of a tile axis only A carries (when there is one): the warps of a CTA then work on the
+// same rows and the same entries of B and C at about the same time, and all but the first of them hit L1.
+template <int MINB>
+__global__ void __launch_bounds__(SBN_TRIPLE_THREADS, MINB) sbn_triple_kernel(const __grid_constant__ SbnTripleParams p) {
+    constexpr int T = SBN_PAIR_T;
+    sbn_pdl_entry();
+    const int rblock = blockIdx.x / p.n_chunks;
+    const int chunk = blockIdx.x % p.n_chunks;
+    const int b = rblock * static_cast<int>(blockDim.x) + threadIdx.x;
+    if (b >= p.n_rows) return;
+    // element offsets fit 32 bits (sbn_pair_fits): strides are scaled by the row pitch once
+    const uint32_t ld = static_cast<uint32_t>(p.ld);
+    const int g = threadIdx.y;
+    const float *const ap = p.a + b + static_cast<uint32_t>(g * p.a_g) * ld;
+    const float *const bp = p.b + b;
+    const float *const cp = p.c + b;
+    float *const op = p.out + b + static_cast<uint32_t>(g * p.o_g) * ld;
+    uint32_t ak[T], aj[T], bj[T], bs[T], ck[T], cz[T];
+#pragma unroll
+    for (int d = 0; d < T; ++d) {
+        ak[d] = static_cast<uint32_t>(d * p.a_k) * ld, aj[d] = static_cast<uint32_t>(d * p.a_j) * ld;
+        bj[d] = static_cast<uint32_t>(d * p.b_j) * ld, bs[d] = static_cast<uint32_t>(d * p.b_s) * ld;
+        ck[d] = static_cast<uint32_t>(d * p.c_k) * ld, cz[d] = static_cast<uint32_t>(d * p.c_z) * ld;
+    }
+    const uint32_t oz = static_cast<uint32_t>(p.o_z) * ld, os = static_cast<uint32_t>(p.o_s) * ld;
+    const int t_begin = chunk * p.tiles_per_cta;
+    const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int4 row = __ldg(reinterpret_cast<const int4 *>(p.tile_off) + t);
+        float acc[T][T];  // [z][s]
+#pragma unroll
+        for (int z = 0; z < T; ++z)
+#pragma unroll
+            for (int s = 0; s < T; ++s) acc[z][s] = 0.f;
+#pragma unroll 1
+        for (int pp = 0; pp < T; ++pp) {
+            // the 75 entries of this p, in flight together
+            float A[T][T], B[T][T], C[T][T];  // A[k][j]  B[j][s]  C[k][z]
+            const uint32_t a0 = static_cast<uint32_t>(row.y + pp * p.a_p) * ld, b0 = static_cast<uint32_t>(row.z + pp * p.b_p) * ld,
+                           c0 = static_cast<uint32_t>(row.w + pp * p.c_p) * ld;
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+#pragma unroll
+                for (int s = 0; s < T; ++s) B[j][s] = bp[b0 + bj[j] + bs[s]];
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+#pragma unroll
+                for (int j = 0; j < T; ++j) A[k][j] = ap[a0 + ak[k] + aj[j]];
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+#pragma unroll
+                for (int z = 0; z < T; ++z) C[k][z] = cp[c0 + ck[k] + cz[z]];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                float n[T];  // N[k][s] = sum_j A[k][j] B[j][s]
+#pragma unroll
+                for (int s = 0; s < T; ++s) {
+                    float v = A[k][0] * B[0][s];
+#pragma unroll
+                    for (int j = 1; j < T; ++j) v = fmaf(A[k][j], B[j][s], v);
+                    n[s] = v;
+                }
+#pragma unroll
+                for (int z = 0; z < T; ++z)
+#pragma unroll
+                    for (int s = 0; s < T; ++s) acc[z][s] = fmaf(C[k][z], n[s], acc[z][s]);
+            }
+        }
+#pragma unroll
+        for (int z = 0; z < T; ++z)
+#pragma unroll
+            for (int s = 0; s < T; ++s) __stcs(op + (static_cast<uint32_t>(row.x) * ld + z * oz + s * os), acc[z][s]);
     }
 }
 
@@ -350,6 +430,109 @@ int64_t tile_slab(const CanonSpec &cs, const std::vector<int> &r, const std::vec
     return o * cs.slab;
 }
 
+// The expanding-product pattern (sbn_pair.h, SbnTripleParams) for two consecutive launched steps; appends the tile table.
+SbnPair *plan_triple(sbn_program *P, int i1, int i2, std::vector<int32_t> *tiles) {
+    constexpr int T = SBN_PAIR_T;
+    const StepDesc &s1 = P->steps[i1], &s2 = P->steps[i2];
+    if (s1.kind != 1 || s2.kind != 1 || s1.ecards.size() != 1 || s2.ecards.size() != 2) return nullptr;
+    if (s1.in.size() != 2 || s2.in.size() != 2 || s1.ecards[0] != T || s2.ecards[0] != T || s2.ecards[1] != T) return nullptr;
+    for (const InDesc &in : s1.in)
+        if (!in.batched || !in.is_slot || !in.ev.empty()) return nullptr;
+    for (const InDesc &in : s2.in)
+        if (!in.batched || !in.is_slot || !in.ev.empty()) return nullptr;
+    int mi = -1;
+    for (int i = 0; i < 2; ++i)
+        if (s2.in[i].id == s1.out_slot) mi = i;
+    if (mi < 0 || s2.in[1 - mi].id == s1.out_slot || s1.out_slot == P->post_slot) return nullptr;
+    const InDesc &M = s2.in[mi], &C = s2.in[1 - mi];
+    // the two variables step 2 sums out, as axes of the intermediate
+    const int je[2] = {axis_of_stride(s1.cards, M.estrides[0]), axis_of_stride(s1.cards, M.estrides[1])};
+    if (je[0] < 0 || je[1] < 0 || je[0] == je[1]) return nullptr;
+    // k: summed out by step 2, carried by exactly one operand of step 1 (that operand is "A"); p: the other one
+    int ai = -1, kk = -1;
+    for (int e = 0; e < 2 && ai < 0; ++e)
+        for (int i = 0; i < 2; ++i)
+            if (s1.in[i].strides[je[e]] != 0 && s1.in[1 - i].strides[je[e]] == 0) ai = i, kk = e;
+    if (ai < 0) return nullptr;
+    const InDesc &A = s1.in[ai], &B = s1.in[1 - ai];
+    const int jk = je[kk], jp = je[1 - kk];
+    if (A.estrides[0] == 0 || B.estrides[0] == 0) return nullptr;
+    // output axes: s = carried by B only, z = new in step 2 (C only); everything else is a tile axis
+    const int n2 = static_cast<int>(s2.cards.size());
+    std::vector<int> to1(n2, -1);
+    int ks = -1, kz = -1;
+    for (int k = 0; k < n2; ++k) {
+        if (M.strides[k] == 0) {
+            if (kz < 0 && s2.cards[k] == T && C.strides[k] != 0) kz = k;
+            continue;
+        }
+        to1[k] = axis_of_stride(s1.cards, M.strides[k]);
+        if (to1[k] < 0 || to1[k] == jk || to1[k] == jp || s1.cards[to1[k]] != s2.cards[k]) return nullptr;
+        if (ks < 0 && s2.cards[k] == T && A.strides[to1[k]] == 0 && B.strides[to1[k]] != 0 && C.strides[k] == 0) ks = k;
+    }
+    if (ks < 0 || kz < 0) return nullptr;
+    const int out_slot = s2.out_slot;
+    if (out_slot == A.id || out_slot == B.id || out_slot == C.id) return nullptr;
+    // a tile axis only A carries (T states) is walked inside the thread: B and C are loaded once for its T tiles
+    static const bool grouped = [] {
+        const char *e = getenv("SOROBN_B200_TRIPLE_GROUP");
+        return e ? atoi(e) != 0 : true;
+    }();
+    int kg = -1;
+    for (int k = 0; k < n2 && grouped && kg < 0; ++k)
+        if (k != ks && k != kz && to1[k] >= 0 && s2.cards[k] == T && A.strides[to1[k]] != 0 && B.strides[to1[k]] == 0 &&
+            C.strides[k] == 0)
+            kg = k;
+    int64_t n_tiles = 1;
+    std::vector<int> r2;
+    for (int k = 0; k < n2; ++k)
+        if (k != ks && k != kz && k != kg) r2.push_back(k), n_tiles *= s2.cards[k];
+    if (n_tiles >= (1LL << 27)) return nullptr;
+
+    SbnPair *pr = new SbnPair();
+    memset(&pr->q, 0, sizeof pr->q);
+    memset(&pr->t, 0, sizeof pr->t);
+    pr->kind = 1;
+    pr->step1 = i1, pr->step2 = i2;
+    pr->a_in = ai, pr->b_in = 1 - ai, pr->c_in = 1 - mi;
+    pr->tile_off_pos = static_cast<int64_t>(tiles->size());
+    SbnTripleParams &q = pr->t;
+    q.n_tiles = static_cast<int32_t>(n_tiles);
+    q.a_j = A.estrides[0], q.a_k = A.strides[jk], q.a_p = A.strides[jp];
+    q.b_j = B.estrides[0], q.b_s = B.strides[to1[ks]], q.b_p = B.strides[jp];
+    q.c_k = C.estrides[kk], q.c_p = C.estrides[1 - kk], q.c_z = C.strides[kz];
+    int64_t os = 1;
+    std::vector<int64_t> os2(n2);
+    for (int k = 0; k < n2; ++k) os2[k] = os, os *= s2.cards[k];
+    q.o_z = static_cast<int32_t>(os2[kz]);
+    q.o_s = static_cast<int32_t>(os2[ks]);
+    q.group = kg >= 0 ? T : 1;
+    q.o_g = kg >= 0 ? static_cast<int32_t>(os2[kg]) : 0;
+    q.a_g = kg >= 0 ? A.strides[to1[kg]] : 0;
+    std::vector<int> dig(r2.size(), 0);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        int64_t ob = 0, ab = 0, bb = 0, cb = 0;
+        for (size_t k = 0; k < r2.size(); ++k) {
+            const int ax = r2[k];
+            ob += dig[k] * os2[ax];
+            cb += static_cast<int64_t>(dig[k]) * C.strides[ax];
+            if (to1[ax] >= 0) {
+                ab += static_cast<int64_t>(dig[k]) * A.strides[to1[ax]];
+                bb += static_cast<int64_t>(dig[k]) * B.strides[to1[ax]];
+            }
+        }
+        tiles->push_back(static_cast<int32_t>(ob));
+        tiles->push_back(static_cast<int32_t>(ab));
+        tiles->push_back(static_cast<int32_t>(bb));
+        tiles->push_back(static_cast<int32_t>(cb));
+        for (size_t k = 0; k < dig.size(); ++k) {
+            if (++dig[k] < s2.cards[r2[k]]) break;
+            dig[k] = 0;
+        }
+    }
+    return pr;
+}
+
 }  // namespace
 
 cudaError_t sbn_pair_set_attrs() {
@@ -376,6 +559,11 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
         return e ? atoi(e) : 4;
     }();
 
+    static const bool triples_on = [] {
+        const char *e = getenv("SOROBN_B200_TRIPLE");
+        return e ? atoi(e) != 0 : true;
+    }();
+
     HostTables H;
     std::vector<float> canon;
     std::vector<int32_t> tiles;
@@ -390,6 +578,14 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
         while (i2 < n_steps && !launched(i2)) ++i2;
         if (i2 >= n_steps) break;
         const StepDesc &s1 = P->steps[i1], &s2 = P->steps[i2];
+        if (triples_on) {
+            if (SbnPair *tr = plan_triple(P, i1, i2, &tiles)) {
+                P->pair_first[i1] = static_cast<int>(P->pairs.size());
+                P->pair_first[i2] = -2;
+                P->pairs.push_back(tr);
+                continue;
+            }
+        }
         if (s1.kind != 1 || s2.kind != 1 || s1.ecards.size() != 1 || s2.ecards.size() != 1) continue;
         if (s1.tile == 0 || s2.tile == 0) continue;  // keep to the steps the tiled kernel covers
         // the frontier F of step 1, the intermediate as an operand of step 2
@@ -453,6 +649,8 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
 
             SbnPair *pr = new SbnPair();
             memset(&pr->q, 0, sizeof pr->q);
+            memset(&pr->t, 0, sizeof pr->t);
+            pr->kind = 0;
             pr->step1 = i1, pr->step2 = i2, pr->f_in = fi;
             pr->m1 = mode_of(c1.layout), pr->m2 = mode_of(c2.layout);
             pr->canon_pos = static_cast<int64_t>(canon.size());
@@ -508,17 +706,65 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
         }
     }
     if (P->pairs.empty()) return cudaSuccess;
-    err = cudaMalloc(&P->d_pair_canon, canon.size() * 4);
+    err = cudaMalloc(&P->d_pair_canon, std::max<size_t>(canon.size(), 4) * 4);
     if (err != cudaSuccess) return err;
     err = cudaMalloc(&P->d_pair_tiles, tiles.size() * 4);
     if (err != cudaSuccess) return err;
-    err = cudaMemcpy(P->d_pair_canon, canon.data(), canon.size() * 4, cudaMemcpyHostToDevice);
+    if (!canon.empty()) err = cudaMemcpy(P->d_pair_canon, canon.data(), canon.size() * 4, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) return err;
     return cudaMemcpy(P->d_pair_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice);
 }
 
+static cudaError_t triple_launch(sbn_program *P, const SbnPair &pr, int64_t n_rows, cudaStream_t stream) {
+    SbnTripleParams q = pr.t;
+    const StepDesc &s1 = P->steps[pr.step1], &s2 = P->steps[pr.step2];
+    q.a = P->slots[s1.in[pr.a_in].id].ptr;
+    q.b = P->slots[s1.in[pr.b_in].id].ptr;
+    q.c = P->slots[s2.in[pr.c_in].id].ptr;
+    q.out = P->slots[s2.out_slot].ptr;
+    q.ld = P->ld;
+    q.n_rows = static_cast<int32_t>(n_rows);
+    q.tile_off = P->d_pair_tiles + pr.tile_off_pos;
+    // with a group axis: 32 rows x T group digits per CTA; without: 128 rows
+    const int rows_per_cta = q.group > 1 ? 32 : 128;
+    const int64_t n_rblocks = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    // few tiles per CTA: the CTAs resident together then cover few row blocks, whose operands stay in L2 for the
+    // re-reads by the other tiles
+    static const int64_t tpc_env = [] {
+        const char *e = getenv("SOROBN_B200_TRIPLE_TPC");
+        return e ? atoll(e) : 1LL;
+    }();
+    // measured on B200 (grid, 100k rows): 3 CTAs / SM (128 registers) 440-453 us, 2 CTAs (152 registers) 464-515 us
+    static const int minb = [] {
+        const char *e = getenv("SOROBN_B200_TRIPLE_MINB");
+        return e ? atoi(e) : 3;
+    }();
+    const int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(q.n_tiles, tpc_env));
+    q.tiles_per_cta = static_cast<int32_t>(tpc);
+    q.n_chunks = static_cast<int32_t>((q.n_tiles + tpc - 1) / tpc);
+    const int64_t grid = q.n_chunks * n_rblocks;
+    if (grid >= (1LL << 31)) return cudaErrorInvalidConfiguration;
+    const dim3 g(static_cast<unsigned>(grid)), b(rows_per_cta, q.group);
+    if (minb == 3) sbn_launch(sbn_triple_kernel<3>, g, b, 0, stream, q);
+    else if (minb == 1) sbn_launch(sbn_triple_kernel<1>, g, b, 0, stream, q);
+    else sbn_launch(sbn_triple_kernel<2>, g, b, 0, stream, q);
+    return cudaGetLastError();
+}
+
+bool sbn_pair_fits(const sbn_program *P, const SbnPair &pr) {
+    // the kernels index their operands with 32-bit element offsets: entries x row pitch must stay below 2^31
+    const StepDesc &s1 = P->steps[pr.step1], &s2 = P->steps[pr.step2];
+    int64_t entries = P->slots[s2.out_slot].size;
+    for (const InDesc &in : s1.in)
+        if (in.batched) entries = std::max(entries, P->slots[in.id].size);
+    for (const InDesc &in : s2.in)
+        if (in.batched && in.id != s1.out_slot) entries = std::max(entries, P->slots[in.id].size);
+    return entries * P->ld < (1LL << 31);
+}
+
 cudaError_t sbn_pair_launch(sbn_program *P, const SbnPair &pr, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows,
                             cudaStream_t stream) {
+    if (pr.kind == 1) return triple_launch(P, pr, n_rows, stream);
     SbnPairParams q = pr.q;
     const StepDesc &s1 = P->steps[pr.step1], &s2 = P->steps[pr.step2];
     q.f = P->slots[s1.in[pr.f_in].id].ptr;

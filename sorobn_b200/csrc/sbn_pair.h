@@ -34,6 +34,7 @@
 #define SBN_PAIR_PW 8             // coefficients per innermost row (T padded to two float4)
 #define SBN_PAIR_MAX_EV 4         // evidence columns the tables of one step may gather
 #define SBN_PAIR_ROWS 256         // evidence rows per CTA
+#define SBN_TRIPLE_THREADS 160    // CTA of the expanding-product pattern: 32 rows x 5 group digits, or 128 rows x 1
 #define SBN_PAIR_SMEM_MAX (40 * 1024)
 
 // evidence columns one canonical array is indexed by: float offset = sum_k min(code_k, card_k - 1) * stride_k
@@ -70,12 +71,40 @@ struct SbnPairParams {
 // step's operand first (25 scalar loads) and the main coefficients stay a broadcast.
 enum SbnPairMode { SBN_PAIR_B = 0, SBN_PAIR_CU = 1, SBN_PAIR_CE = 2 };
 
+// Second pattern: an expanding product and the contraction that consumes it,
+//
+//     mid[a.., p, k, s, q..] = sum_j A[a.., p, k, j] B[p, q.., j, s]        (e.g. 3125 <- B625 x B625)
+//     out[a.., z, s, q..]    = sum_{p, k} C[k, q.., z, p] mid[a.., p, k, s, q..]   (625 <- sum_25 B625 x B3125)
+//
+// all operands batched, no tables.  The 3125-entry intermediate costs 25,000 B per row to write and read back;
+// a thread that owns one row and one combination of the untouched axes (a.., q..) walks p, and per p computes
+// N[k][s] = sum_j A[k][j] B[j][s] and out[z][s] += sum_k C[k][z] N[k][s] from 75 loaded entries -- the
+// intermediate never exists.  The operands are re-read once per combination of the axes they lack (from L2: CTAs
+// that are resident together work on the same row blocks).
+struct SbnTripleParams {
+    const float *a, *b, *c;
+    float *out;
+    const int32_t *tile_off;      // [n_tiles][4] = out entry, A entry, B entry, C entry
+    int64_t ld;
+    int32_t n_rows;
+    int32_t n_tiles, tiles_per_cta, n_chunks;
+    int32_t a_p, a_k, a_j;        // entry strides
+    int32_t b_p, b_j, b_s;
+    int32_t c_p, c_k, c_z;
+    int32_t o_z, o_s;
+    int32_t group;                // 1, or T: threadIdx.y walks the T digits of a tile axis only A carries ...
+    int32_t a_g, o_g;             // ... with these entry strides in A and in the output
+};
+
 // One planned pair (host side).
 struct SbnPair {
+    int kind;                     // 0: two table x frontier steps (SbnPairParams); 1: expanding product + contraction (SbnTripleParams)
     int step1, step2;             // indices into sbn_program::steps
     int f_in;                     // index of the batched operand among step1's inputs
     int m1, m2;                   // SbnPairMode of the two steps
     SbnPairParams q;              // everything but the run-time pointers
+    SbnTripleParams t;
+    int a_in, b_in, c_in;         // kind 1: operand indices (A, B among step1's inputs, C among step2's)
     int64_t tile_off_pos;         // int32 offset into the pair tile table
     int64_t canon_pos;            // float offset into the canonical coefficient buffer
 };
@@ -85,5 +114,8 @@ struct sbn_program;
 cudaError_t sbn_pair_plan(sbn_program *P);
 cudaError_t sbn_pair_launch(sbn_program *P, const SbnPair &pr, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows,
                             cudaStream_t stream);
+// false when the reserved row pitch is too large for the kernels' 32-bit element offsets: the two steps then run
+// as separate launches
+bool sbn_pair_fits(const sbn_program *P, const SbnPair &pr);
 cudaError_t sbn_pair_set_attrs();
 void sbn_pair_free(sbn_program *P);

@@ -72,6 +72,8 @@ def load():
     lib.sbn_program_run_host.argtypes = [vp, vp, i64, i64, vp, i64]
     lib.sbn_program_run_device.restype = i32
     lib.sbn_program_run_device.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+    lib.sbn_program_step_roles.restype = i32
+    lib.sbn_program_step_roles.argtypes = [vp, vp, i64]
     lib.sbn_program_profile.restype = i32
     lib.sbn_program_profile.argtypes = [vp, vp, i64, i64, vp, i64, vp, vp, i64]
     lib.sbn_program_info.restype = i32
@@ -104,6 +106,7 @@ EXPORTS = (
     "sbn_abi_version", "sbn_last_error", "sbn_device_count", "sbn_program_create", "sbn_program_create_f64",
     "sbn_program_run_host_f64", "sbn_program_evidence_host", "sbn_program_evidence_host_f64", "sbn_program_destroy",
     "sbn_program_reserve", "sbn_program_run_host", "sbn_program_run_device", "sbn_program_profile",
+    "sbn_program_step_roles",
     "sbn_program_info", "sbn_program_set_graph", "sbn_program_set_tiled", "sbn_gibbs_create", "sbn_gibbs_run_host",
     "sbn_sampler_run_host", "sbn_gibbs_conditional", "sbn_gibbs_destroy", "sbn_host_alloc", "sbn_host_free",
 )
@@ -245,6 +248,13 @@ class Program:
         """Device path: raw device pointers, asynchronous on `stream`."""
         _check(load().sbn_program_run_device(self._h, ctypes.c_void_p(d_ev), int(ld_ev), int(n_rows),
                                              ctypes.c_void_p(d_out), int(ld_out), ctypes.c_void_p(stream)))
+
+    def step_roles(self) -> np.ndarray:
+        """Per program step: 0 ran once at creation, 1 own launch, 2 / 3 first / second step of a paired launch,
+        4 / 5 expanding product / its consumer as one launch, 6 inside an on-chip segment."""
+        roles = np.zeros(len(self.plan.steps), dtype=np.int32)
+        _check(load().sbn_program_step_roles(self._h, roles.ctypes.data, roles.size))
+        return roles
 
     def profile(self, d_ev: int, ld_ev: int, n_rows: int, d_out: int, ld_out: int, stream: int = 0) -> np.ndarray:
         n = len(self.plan.steps) + 1

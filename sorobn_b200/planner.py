@@ -606,6 +606,13 @@ def _depth_first_order(steps):
     # children always precede their consumer in the incoming list: one forward pass suffices
     for i, st in enumerate(steps):
         kids = sorted(children[i], key=lambda c: (-(peak[c] - size[c]), c))
+        # An expanding product (an output several times the size of its siblings' outputs) goes last, so that its
+        # consumer follows it immediately: the engine can then run the two as one launch (csrc/sbn_pair.h), and the
+        # big intermediate is not held while the other sub-trees are computed.
+        if len(kids) > 1 and os.environ.get("SOROBN_B200_BIG_LAST", "1") == "1":
+            big = max(kids, key=lambda c: size[c])
+            if all(size[big] >= 2 * size[c] for c in kids if c != big):
+                kids = [c for c in kids if c != big] + [big]
         held, worst = 0, 0
         for c in kids:
             worst = max(worst, held + peak[c])

@@ -787,7 +787,9 @@ def test_paired_steps_match_single_step_launches_and_the_oracle(workload, rows):
     assert np.allclose(paired, single, rtol=3e-6, atol=1e-30)
     assert prog.info()["pairs"] == n_single - n_paired and prog.info()["pair_bytes_saved_per_row"] >= 8 * prog.info()["pairs"]
     if workload == "grid10x10":
-        assert n_single - n_paired >= 7, (n_single, n_paired)  # the frontier chains of the grid pair up
+        assert n_single - n_paired >= 8, (n_single, n_paired)  # the frontier chains of the grid pair up
+        # ... and the expanding product 3125 <- B625 x B625 runs inside its consumer: 25,000 B per row on its own
+        assert prog.info()["pair_bytes_saved_per_row"] >= 8 * 3125 + 7 * 8 * 625, prog.info()
         assert not np.array_equal(paired, single)
     prog.set_graph(True)
     assert np.array_equal(prog.run(codes, rows), paired)  # the captured graph replays the same launches

@@ -381,3 +381,23 @@ def test_merged_sum_outs_with_lifted_evidence_match_the_oracle(trial):
         _, got = run_plan(bn, query, evs, codes, planner.MODE_BATCHED, merge_sum_outs=True, lift_evidence=True,
                           fuse_elims=fuse)
         assert np.allclose(got, want, rtol=1e-12, atol=0), (trial, fuse)
+
+
+def test_slots_and_order_allow_two_steps_per_launch():
+    """What the engine's paired launches (csrc/sbn_pair.h) rely on: a batched step never writes the
+    buffer an operand of the PREVIOUS batched step lives in (the fused launch reads that operand while
+    it writes this output), and an expanding product is immediately followed by its consumer."""
+    for name in ("grid10x10", "dag50", "asia_1m"):
+        wl = workloads.WORKLOADS[name]()
+        net = wl.build()._compiled
+        plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+        batched = [st for st in plan.steps if st.kind == planner.KIND_BATCHED]
+        for prev, st in zip(batched, batched[1:]):
+            held = {f.buf for f, _, _ in prev.inputs if f.is_slot and f.batched}
+            held |= {f.buf for f, _, _ in st.inputs if f.is_slot and f.batched}
+            assert st.out_slot not in held, (name, st.out_slot, held)
+        if name == "grid10x10":
+            sizes = [int(np.prod(st.cards)) for st in batched]
+            big = sizes.index(3125)
+            consumer = batched[big + 1]
+            assert any(f.is_slot and f.batched and f.buf == batched[big].out_slot for f, _, _ in consumer.inputs)

@@ -60,10 +60,11 @@ traffic = {}
 if os.path.exists(traffic_path):
     traffic = json.load(open(traffic_path))
 dom = max(by_kernel.items(), key=lambda kv: kv[1]["us"])
-steps_only = {k: v for k, v in by_kernel.items() if k.startswith("sbn_step") or k.startswith("sbn_pair")}
+steps_only = {k: v for k, v in by_kernel.items() if k.startswith(("sbn_step_tiled", "sbn_step_batched", "sbn_pair", "sbn_triple"))}
 traffic[workload] = {
     "dram_bytes_per_step": sum(v["dram_bytes"] for v in steps_only.values()),
     "launches_per_step": sum(v["launches"] for v in steps_only.values()),
+    "by_kernel": {k: {"launches": v["launches"], "dram_bytes": v["dram_bytes"], "us": v["us"]} for k, v in steps_only.items()},
     "dominant_kernel": dom[0], "dominant_dram_bytes_per_step": dom[1]["dram_bytes"],
     "dominant_launches_per_step": dom[1]["launches"],
     "source": "profiles/" + os.path.basename(prefix) + f"_launches_{workload}.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
