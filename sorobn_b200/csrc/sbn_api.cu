@@ -732,7 +732,8 @@ inline bool chain_on(const sbn_program *P) {
 }
 
 inline bool pair_on(const sbn_program *P) {
-    return P->use_pair && P->use_tiled && !P->use_branches && !chain_on(P) && !P->pairs.empty();
+    // with the on-chip segments running, only pairs that were planned around them (SOROBN_B200_CHAIN=1 at creation)
+    return P->use_pair && P->use_tiled && !P->use_branches && (!chain_on(P) || P->pairs_avoid_segments) && !P->pairs.empty();
 }
 
 inline bool graph_allowed(const sbn_program *P) { return P->use_graph; }

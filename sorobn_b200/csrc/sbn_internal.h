@@ -130,5 +130,6 @@ struct sbn_program {
     float *d_pair_canon = nullptr;   // canonical coefficient arrays of all pairs
     int32_t *d_pair_tiles = nullptr; // their tile tables
     bool use_pair = true;
+    bool pairs_avoid_segments = false;  // planned with the on-chip segments switched on: no pair touches a segment's step
 };
 

@@ -35,9 +35,15 @@ __device__ __forceinline__ void pair_ev_offsets(const SbnPairParams &p, const Sb
 
 // One step on a register tile: acc[d0][d1] = sum_x in[x][d0] * coef[x][d0][d1]   (mode B: coef[x][d1]).
 // `k` points at the main array of this tile, `e` holds the per-row offsets into it.
+struct PairG {  // a batched coefficient operand (modes GB / GC): row pointer, tile base and pre-scaled strides
+    const float *p;
+    uint32_t base;
+    uint32_t x[SBN_PAIR_T], d0[SBN_PAIR_T], d1[SBN_PAIR_T];
+};
+
 template <int MODE, int V>
 __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR_T][V], float (&acc)[SBN_PAIR_T][SBN_PAIR_T][V],
-                                          const float *k, const int (&e)[V]) {
+                                          const float *k, const int (&e)[V], const PairG &G) {
     constexpr int T = SBN_PAIR_T, PW = SBN_PAIR_PW;
 #pragma unroll
     for (int d0 = 0; d0 < T; ++d0)
@@ -51,6 +57,14 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
         if constexpr (MODE == SBN_PAIR_B) {
 #pragma unroll
             for (int l = 0; l < V; ++l) pair_coef8(c[l], k + e[l] + x * PW);
+        } else if constexpr (MODE == SBN_PAIR_GB) {
+#pragma unroll
+            for (int d1 = 0; d1 < T; ++d1) {
+                float r[V];
+                sbn_ldv<V>(r, G.p + (G.base + G.x[x] + G.d1[d1]));
+#pragma unroll
+                for (int l = 0; l < V; ++l) c[l][d1] = r[l];
+            }
         }
 #pragma unroll
         for (int d0 = 0; d0 < T; ++d0) {
@@ -61,6 +75,14 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
                 for (int l = 0; l < V; ++l)
 #pragma unroll
                     for (int d1 = 0; d1 < T; ++d1) c[l][d1] = k[e[l] + (x * T + d0) * T + d1];
+            } else if constexpr (MODE == SBN_PAIR_GC) {
+#pragma unroll
+                for (int d1 = 0; d1 < T; ++d1) {
+                    float r[V];
+                    sbn_ldv<V>(r, G.p + (G.base + G.x[x] + G.d0[d0] + G.d1[d1]));
+#pragma unroll
+                    for (int l = 0; l < V; ++l) c[l][d1] = r[l];
+                }
             }
 #pragma unroll
             for (int d1 = 0; d1 < T; ++d1)
@@ -77,9 +99,10 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
 // Coefficients past a real cardinality are zero, F indices past one are clamped: the loop nest is
 // always T x T x T and only the stores are predicated.
 // Five CTAs per SM (96 registers, a handful of spilled bytes): measured on B200, grid 100k rows, 2 / 3 / 4 / 5 / 6 / 8
-// resident CTAs -> 2.65 / 2.65 / 2.57 / 2.52 / 2.60 / 2.92 ms per step.
+// resident CTAs -> 2.65 / 2.65 / 2.57 / 2.52 / 2.60 / 2.92 ms per step.  (Four with a batched coefficient operand: its
+// fifteen pre-scaled offsets would spill at 96 registers.)
 template <int M1, int M2>
-__global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const __grid_constant__ SbnPairParams p) {
+__global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, (M1 >= SBN_PAIR_GB ? 4 : 5)) sbn_pair_kernel(const __grid_constant__ SbnPairParams p) {
     constexpr int T = SBN_PAIR_T, V = kV;
     extern __shared__ __align__(16) float s_canon[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -122,6 +145,17 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
         ow[d] = static_cast<uint32_t>(d * p.o_sw) * ld;
         oz[d] = static_cast<uint32_t>(d * p.o_sz) * ld;
     }
+    PairG G;
+    G.p = p.g + b;
+    G.base = 0;
+    if constexpr (M1 == SBN_PAIR_GB || M1 == SBN_PAIR_GC) {
+#pragma unroll
+        for (int d = 0; d < T; ++d) {
+            G.x[d] = static_cast<uint32_t>(d * p.g_x) * ld;
+            G.d0[d] = static_cast<uint32_t>(d * p.g_y) * ld;
+            G.d1[d] = static_cast<uint32_t>(d * p.g_w) * ld;
+        }
+    }
     const int t_begin = chunk * p.tiles_per_cta;
     const int t_end = min(p.n_tiles, t_begin + p.tiles_per_cta);
 
@@ -146,7 +180,8 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
                     for (int l = 0; l < V; ++l) f[x][y][l] *= k[g1[l] + x * T + y];
         }
         float mid[T][T][V];
-        pair_step<M1, V>(f, mid, s_canon + r0.z, e1);
+        if constexpr (M1 == SBN_PAIR_GB || M1 == SBN_PAIR_GC) G.base = static_cast<uint32_t>(r1.z) * ld;
+        pair_step<M1, V>(f, mid, s_canon + r0.z, e1, G);
         if (p.has_pre2) {
             const float *const k = s_canon + r1.y;
 #pragma unroll
@@ -157,7 +192,7 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, 5) sbn_pair_kernel(const _
                     for (int l = 0; l < V; ++l) mid[y][w][l] *= k[g2[l] + y * T + w];
         }
         float acc[T][T][V];
-        pair_step<M2, V>(mid, acc, s_canon + r0.w, e2);
+        pair_step<M2, V>(mid, acc, s_canon + r0.w, e2, G);
 
 #pragma unroll
         for (int z = 0; z < T; ++z)
@@ -259,6 +294,12 @@ void launch_modes(const SbnPair &pr, const SbnPairParams &q, unsigned grid, size
         SBN_PAIR_CASE(2, 0)
         SBN_PAIR_CASE(2, 1)
         SBN_PAIR_CASE(2, 2)
+        SBN_PAIR_CASE(3, 0)
+        SBN_PAIR_CASE(3, 1)
+        SBN_PAIR_CASE(3, 2)
+        SBN_PAIR_CASE(4, 0)
+        SBN_PAIR_CASE(4, 1)
+        SBN_PAIR_CASE(4, 2)
     }
 #undef SBN_PAIR_CASE
 }
@@ -494,6 +535,7 @@ SbnPair *plan_triple(sbn_program *P, int i1, int i2, std::vector<int32_t> *tiles
     memset(&pr->t, 0, sizeof pr->t);
     pr->kind = 1;
     pr->step1 = i1, pr->step2 = i2;
+    pr->g_in = -1;
     pr->a_in = ai, pr->b_in = 1 - ai, pr->c_in = 1 - mi;
     pr->tile_off_pos = static_cast<int64_t>(tiles->size());
     SbnTripleParams &q = pr->t;
@@ -572,11 +614,14 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
 
     const int n_steps = static_cast<int>(P->steps.size());
     auto launched = [&](int i) { return P->steps[i].kind != 0; };  // table steps ran when the program was created
+    P->pairs_avoid_segments = P->use_chain && !P->segments.empty();
+    auto in_segment = [&](int i) { return P->pairs_avoid_segments && P->seg_first[i] != -1; };
     for (int i1 = 0; i1 < n_steps; ++i1) {
         if (!launched(i1) || P->pair_first[i1] != -1) continue;
         int i2 = i1 + 1;
         while (i2 < n_steps && !launched(i2)) ++i2;
         if (i2 >= n_steps) break;
+        if (in_segment(i1) || in_segment(i2)) continue;
         const StepDesc &s1 = P->steps[i1], &s2 = P->steps[i2];
         if (triples_on) {
             if (SbnPair *tr = plan_triple(P, i1, i2, &tiles)) {
@@ -589,14 +634,26 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
         if (s1.kind != 1 || s2.kind != 1 || s1.ecards.size() != 1 || s2.ecards.size() != 1) continue;
         if (s1.tile == 0 || s2.tile == 0) continue;  // keep to the steps the tiled kernel covers
         // the frontier F of step 1, the intermediate as an operand of step 2
-        int fi = -1, mi = -1, n_b1 = 0, n_b2 = 0;
+        int fi = -1, gi = -1, mi = -1, n_b1 = 0, n_b2 = 0;
         for (int i = 0; i < static_cast<int>(s1.in.size()); ++i)
-            if (s1.in[i].batched) fi = i, ++n_b1;
+            if (s1.in[i].batched) gi = fi, fi = i, ++n_b1;
         for (int i = 0; i < static_cast<int>(s2.in.size()); ++i)
             if (s2.in[i].batched) mi = i, ++n_b2;
-        if (n_b1 != 1 || n_b2 != 1) continue;
-        const InDesc &F = s1.in[fi], &M = s2.in[mi];
-        if (!M.is_slot || M.id != s1.out_slot || !M.ev.empty() || !F.ev.empty()) continue;
+        if (n_b1 < 1 || n_b1 > 2 || n_b2 != 1) continue;
+        const InDesc &M = s2.in[mi];
+        if (!M.is_slot || M.id != s1.out_slot || !M.ev.empty()) continue;
+        if (n_b1 == 2) {
+            // a second batched operand G supplies step 1's coefficients (modes GB / GC): no tables beside it, and F is
+            // the operand that carries the variable step 2 sums out
+            if (s1.in.size() != 2) continue;
+            const int jy0 = axis_of_stride(s1.cards, M.estrides[0]);
+            if (jy0 < 0) continue;
+            if (s1.in[fi].strides[jy0] == 0 || (s1.in[gi].strides[jy0] != 0 && P->slots[s1.in[gi].id].size > P->slots[s1.in[fi].id].size))
+                std::swap(fi, gi);
+            if (!s1.in[gi].is_slot || !s1.in[gi].ev.empty() || s1.in[gi].id == s2.out_slot) continue;
+        }
+        const InDesc &F = s1.in[fi];
+        if (!F.ev.empty()) continue;
         // the launch reads F while it writes the second step's output: never the same buffer
         // (planner.py `_assign_slots` releases a step's operands one step late for this)
         if (!F.is_slot || F.id == s2.out_slot || s1.out_slot == P->post_slot) continue;
@@ -626,13 +683,16 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
             if (kw == kz) continue;
             const int jw = to1[kw];
             if (F.strides[jw] != 0 || s1.cards[jw] > T || s1.cards[jw] < min_card) continue;
+            if (gi >= 0 && (s1.in[gi].strides[jw] == 0 || s1.in[gi].estrides[0] == 0 || cx != T || cy != T || s1.cards[jw] != T))
+                continue;  // G must carry w and x, and is not padded: exact cardinalities
             std::vector<int> r2, r1;  // untouched axes, as axes of out2 / of out1
             int64_t n_tiles = 1;
             for (int k = 0; k < n2; ++k)
                 if (k != kw && k != kz) r2.push_back(k), r1.push_back(to1[k]), n_tiles *= s2.cards[k];
             if (n_tiles >= (1LL << 27)) continue;
             CanonSpec c1, g1, c2, g2;
-            if (!spec_step(s1, fi, jy, jw, r1, &c1, &g1) || !spec_step(s2, mi, kw, kz, r2, &c2, &g2)) continue;
+            if (gi < 0 && !spec_step(s1, fi, jy, jw, r1, &c1, &g1)) continue;
+            if (!spec_step(s2, mi, kw, kz, r2, &c2, &g2)) continue;
             const int64_t total = c1.floats() + c2.floats() + g1.floats() + g2.floats();
             if (total * 4 > SBN_PAIR_SMEM_MAX) continue;
             if (!fetched) {
@@ -651,8 +711,9 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
             memset(&pr->q, 0, sizeof pr->q);
             memset(&pr->t, 0, sizeof pr->t);
             pr->kind = 0;
-            pr->step1 = i1, pr->step2 = i2, pr->f_in = fi;
+            pr->step1 = i1, pr->step2 = i2, pr->f_in = fi, pr->g_in = gi;
             pr->m1 = mode_of(c1.layout), pr->m2 = mode_of(c2.layout);
+            if (gi >= 0) pr->m1 = s1.in[gi].strides[jy] == 0 ? SBN_PAIR_GB : SBN_PAIR_GC;
             pr->canon_pos = static_cast<int64_t>(canon.size());
             pr->tile_off_pos = static_cast<int64_t>(tiles.size());
             SbnPairParams &q = pr->q;
@@ -672,6 +733,7 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
             for (int k = 0; k < n2; ++k) os2[k] = os, os *= s2.cards[k];
             q.o_sw = static_cast<int32_t>(os2[kw]);
             q.o_sz = static_cast<int32_t>(os2[kz]);
+            if (gi >= 0) q.g_x = s1.in[gi].estrides[0], q.g_y = s1.in[gi].strides[jy], q.g_w = s1.in[gi].strides[jw];
             q.has_pre1 = g1.tabs.empty() ? 0 : 1;
             q.has_pre2 = g2.tabs.empty() ? 0 : 1;
             set_ev(&q.ev_main1, c1);
@@ -692,7 +754,10 @@ cudaError_t sbn_pair_plan(sbn_program *P) {
                 tiles.push_back(static_cast<int32_t>(at_c2 + tile_slab(c2, r2, dig)));
                 tiles.push_back(static_cast<int32_t>(at_g1 + tile_slab(g1, r1, dig)));
                 tiles.push_back(static_cast<int32_t>(at_g2 + tile_slab(g2, r2, dig)));
-                tiles.push_back(0);
+                int64_t gb = 0;
+                if (gi >= 0)
+                    for (size_t k = 0; k < r1.size(); ++k) gb += static_cast<int64_t>(dig[k]) * s1.in[gi].strides[r1[k]];
+                tiles.push_back(static_cast<int32_t>(gb));
                 tiles.push_back(0);
                 for (size_t k = 0; k < dig.size(); ++k) {
                     if (++dig[k] < s2.cards[r2[k]]) break;
@@ -768,6 +833,7 @@ cudaError_t sbn_pair_launch(sbn_program *P, const SbnPair &pr, const uint8_t *d_
     SbnPairParams q = pr.q;
     const StepDesc &s1 = P->steps[pr.step1], &s2 = P->steps[pr.step2];
     q.f = P->slots[s1.in[pr.f_in].id].ptr;
+    q.g = pr.g_in >= 0 ? P->slots[s1.in[pr.g_in].id].ptr : q.f;
     q.out = P->slots[s2.out_slot].ptr;
     q.ev = d_ev;
     q.ld_ev = ld_ev;

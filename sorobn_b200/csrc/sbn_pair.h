@@ -48,7 +48,7 @@ struct SbnPairParams {
     float *out;                   // output of the second step               [entries][ld]
     const uint8_t *ev;
     const float *canon;           // canonical arrays of both steps (global; staged whole)
-    const int32_t *tile_off;      // [n_tiles][8] = out entry, F entry, float offsets of main 1, main 2, pre 1, pre 2, 0, 0
+    const int32_t *tile_off;      // [n_tiles][8] = out entry, F entry, float offsets of main 1, main 2, pre 1, pre 2, G entry, 0
     int64_t ld_ev, ld;
     int32_t n_rows;
     int32_t canon_floats;         // multiple of 4
@@ -58,6 +58,8 @@ struct SbnPairParams {
     int32_t o_sw, o_sz;           // entry strides of w and z in the output
     int32_t has_pre1, has_pre2;   // per-row factors applied to F[x][y] / mid[y][w] before the step's sum
     SbnPairEv ev_main1, ev_main2, ev_pre1, ev_pre2;
+    const float *g;               // modes GB / GC: the second batched operand of step 1, its coefficients [entries][ld]
+    int32_t g_x, g_y, g_w;        // ... and its entry strides (g_y = 0 in mode GB)
 };
 
 // Layout of a step's main coefficient array (chosen per step when the program is created):
@@ -69,7 +71,10 @@ struct SbnPairParams {
 // A table that has evidence axes but not the second tile axis is kept out of the main array when that
 // leaves the main array evidence-free: it becomes the "pre" factor [evidence][r][x][d0] applied to the
 // step's operand first (25 scalar loads) and the main coefficients stay a broadcast.
-enum SbnPairMode { SBN_PAIR_B = 0, SBN_PAIR_CU = 1, SBN_PAIR_CE = 2 };
+// Step 1 only: when its coefficients are a second BATCHED factor G (`625 <- sum_x B125 x B625`, no tables), they are
+// read from global memory, two rows per 64-bit load: GB = G lacks the first tile axis (25 loads per tile), GC = it
+// carries it (125 loads per tile).  G has 5 x fewer entries than F and is re-read once per tile, out of L2.
+enum SbnPairMode { SBN_PAIR_B = 0, SBN_PAIR_CU = 1, SBN_PAIR_CE = 2, SBN_PAIR_GB = 3, SBN_PAIR_GC = 4 };
 
 // Second pattern: an expanding product and the contraction that consumes it,
 //
@@ -101,6 +106,7 @@ struct SbnPair {
     int kind;                     // 0: two table x frontier steps (SbnPairParams); 1: expanding product + contraction (SbnTripleParams)
     int step1, step2;             // indices into sbn_program::steps
     int f_in;                     // index of the batched operand among step1's inputs
+    int g_in;                     // modes GB / GC: index of the second batched operand of step1, else -1
     int m1, m2;                   // SbnPairMode of the two steps
     SbnPairParams q;              // everything but the run-time pointers
     SbnTripleParams t;
