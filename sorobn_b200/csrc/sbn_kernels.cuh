@@ -128,6 +128,25 @@ __device__ __forceinline__ void sbn_pdl_entry() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two evidence rows per issue slot.  Same FP32 rate as two FFMA
+// (tools/micro/ffma2_bench.cu: 71 vs 73 TFLOP/s), half the instructions.
+#ifndef SBN_FFMA2
+#define SBN_FFMA2 1
+#endif
+__device__ __forceinline__ void sbn_fma2(float (&acc)[2], const float (&a)[2], const float (&b)[2]) {
+#if SBN_FFMA2
+    unsigned long long ra, rb, rc;
+    memcpy(&ra, a, 8);
+    memcpy(&rb, b, 8);
+    memcpy(&rc, acc, 8);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+    memcpy(acc, &rc, 8);
+#else
+    acc[0] = fmaf(a[0], b[0], acc[0]);
+    acc[1] = fmaf(a[1], b[1], acc[1]);
+#endif
+}
+
 __device__ __forceinline__ float4 sbn_mul4(float4 a, float4 b) {
     return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
 }
@@ -653,9 +672,14 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA 
 #pragma unroll
                     for (int d0 = 0; d0 < T; ++d0)
 #pragma unroll
-                        for (int d1 = 0; d1 < TB; ++d1)
+                        for (int d1 = 0; d1 < TB; ++d1) {
+                            if constexpr (V == 2) {
+                                sbn_fma2(acc[d0][d1], a[d0], bb[d1]);
+                            } else {
 #pragma unroll
-                            for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                                for (int l = 0; l < V; ++l) acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                            }
+                        }
                 }
               }
             } else {

@@ -45,6 +45,10 @@ template <int MODE, int V>
 __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR_T][V], float (&acc)[SBN_PAIR_T][SBN_PAIR_T][V],
                                           const float *k, const int (&e)[V], const PairG &G) {
     constexpr int T = SBN_PAIR_T, PW = SBN_PAIR_PW;
+    // per-row coefficients that arrive one value (CE) or one row pair (GB / GC) at a time are kept as (row 0, row 1)
+    // register pairs and go through the packed FFMA2; float4 loads (B, CU) fill four registers of ONE row, pairing
+    // them up would cost more moves than the packed FMA saves
+    constexpr bool PACKED = V == 2 && (MODE == SBN_PAIR_CE || MODE == SBN_PAIR_GB || MODE == SBN_PAIR_GC);
 #pragma unroll
     for (int d0 = 0; d0 < T; ++d0)
 #pragma unroll
@@ -53,18 +57,14 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
             for (int l = 0; l < V; ++l) acc[d0][d1][l] = 0.f;
 #pragma unroll
     for (int x = 0; x < T; ++x) {
-        float c[V][PW];
+        float c[V][PW];   // [row][d1]   (B, CU)
+        float cp[T][V];   // [d1][row]   (PACKED)
         if constexpr (MODE == SBN_PAIR_B) {
 #pragma unroll
             for (int l = 0; l < V; ++l) pair_coef8(c[l], k + e[l] + x * PW);
         } else if constexpr (MODE == SBN_PAIR_GB) {
 #pragma unroll
-            for (int d1 = 0; d1 < T; ++d1) {
-                float r[V];
-                sbn_ldv<V>(r, G.p + (G.base + G.x[x] + G.d1[d1]));
-#pragma unroll
-                for (int l = 0; l < V; ++l) c[l][d1] = r[l];
-            }
+            for (int d1 = 0; d1 < T; ++d1) sbn_ldv<V>(cp[d1], G.p + (G.base + G.x[x] + G.d1[d1]));
         }
 #pragma unroll
         for (int d0 = 0; d0 < T; ++d0) {
@@ -72,23 +72,23 @@ __device__ __forceinline__ void pair_step(const float (&in)[SBN_PAIR_T][SBN_PAIR
                 pair_coef8(c[0], k + (x * T + d0) * PW);  // no evidence axis: one broadcast serves every row
             } else if constexpr (MODE == SBN_PAIR_CE) {
 #pragma unroll
-                for (int l = 0; l < V; ++l)
+                for (int d1 = 0; d1 < T; ++d1)
 #pragma unroll
-                    for (int d1 = 0; d1 < T; ++d1) c[l][d1] = k[e[l] + (x * T + d0) * T + d1];
+                    for (int l = 0; l < V; ++l) cp[d1][l] = k[e[l] + (x * T + d0) * T + d1];
             } else if constexpr (MODE == SBN_PAIR_GC) {
 #pragma unroll
-                for (int d1 = 0; d1 < T; ++d1) {
-                    float r[V];
-                    sbn_ldv<V>(r, G.p + (G.base + G.x[x] + G.d0[d0] + G.d1[d1]));
-#pragma unroll
-                    for (int l = 0; l < V; ++l) c[l][d1] = r[l];
-                }
+                for (int d1 = 0; d1 < T; ++d1) sbn_ldv<V>(cp[d1], G.p + (G.base + G.x[x] + G.d0[d0] + G.d1[d1]));
             }
 #pragma unroll
-            for (int d1 = 0; d1 < T; ++d1)
+            for (int d1 = 0; d1 < T; ++d1) {
+                if constexpr (PACKED) {
+                    sbn_fma2(acc[d0][d1], in[x][d0], cp[d1]);
+                } else {
 #pragma unroll
-                for (int l = 0; l < V; ++l)
-                    acc[d0][d1][l] = fmaf(in[x][d0][l], c[MODE == SBN_PAIR_CU ? 0 : l][d1], acc[d0][d1][l]);
+                    for (int l = 0; l < V; ++l)
+                        acc[d0][d1][l] = fmaf(in[x][d0][l], c[MODE == SBN_PAIR_CU ? 0 : l][d1], acc[d0][d1][l]);
+                }
+            }
         }
     }
 }
