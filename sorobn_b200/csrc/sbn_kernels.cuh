@@ -747,14 +747,19 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA 
 #pragma unroll
                     for (int d0 = 0; d0 < T; ++d0)
 #pragma unroll
-                        for (int d1 = 0; d1 < TB; ++d1)
+                        for (int d1 = 0; d1 < TB; ++d1) {
+                            if constexpr (NC == 0 && V == 2) {
+                                sbn_fma2(acc[d0][d1], a[d0], bb[d1]);
+                            } else {
 #pragma unroll
-                            for (int l = 0; l < V; ++l) {
-                                if constexpr (NC > 0)
-                                    acc[d0][d1][l] = fmaf(a[d0][l] * bb[d1][l], rc[d0][d1][l], acc[d0][d1][l]);
-                                else
-                                    acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                                for (int l = 0; l < V; ++l) {
+                                    if constexpr (NC > 0)
+                                        acc[d0][d1][l] = fmaf(a[d0][l] * bb[d1][l], rc[d0][d1][l], acc[d0][d1][l]);
+                                    else
+                                        acc[d0][d1][l] = fmaf(a[d0][l], bb[d1][l], acc[d0][d1][l]);
+                                }
                             }
+                        }
                 }
             }
 #if SBN_FOLD_NORMALISE
