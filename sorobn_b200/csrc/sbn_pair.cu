@@ -824,7 +824,10 @@ bool sbn_pair_fits(const sbn_program *P, const SbnPair &pr) {
         if (in.batched) entries = std::max(entries, P->slots[in.id].size);
     for (const InDesc &in : s2.in)
         if (in.batched && in.id != s1.out_slot) entries = std::max(entries, P->slots[in.id].size);
-    return entries * P->ld < (1LL << 31);
+    // (SOROBN_B200_PAIR_IDX_LIMIT lowers the limit: the tests use it to walk the fallback path with small programs)
+    const char *e = getenv("SOROBN_B200_PAIR_IDX_LIMIT");
+    const int64_t limit = e ? atoll(e) : (1LL << 31);
+    return entries * P->ld < limit;
 }
 
 cudaError_t sbn_pair_launch(sbn_program *P, const SbnPair &pr, const uint8_t *d_ev, int64_t ld_ev, int64_t n_rows,

@@ -802,3 +802,45 @@ def test_paired_steps_match_single_step_launches_and_the_oracle(workload, rows):
     p_pair = prog.evidence(codes, rows)
     prog.set_tiled(10)
     assert np.allclose(p_pair, prog.evidence(codes, rows), rtol=3e-6, atol=0)
+
+
+def test_step_roles_and_the_fallback_when_offsets_do_not_fit_32_bits(monkeypatch):
+    """`sbn_program_step_roles` names how each step runs; on the benchmark grid: pairs, one expanding
+    product fused with its consumer, table steps hoisted to creation.  A program whose `entries x row
+    pitch` exceeds the fused kernels' 32-bit element offsets must fall back to one launch per step
+    (here forced with SOROBN_B200_PAIR_IDX_LIMIT) and give the numbers of `set_tiled(10)`."""
+    from sorobn_b200 import engine, planner, workloads
+
+    wl = workloads.grid10x10()
+    bn = wl.build()
+    net = bn._compiled
+    plan = planner.build_plan(net, [net.index[q] for q in wl.query], [net.index[e] for e in wl.evidence])
+    rows = 3001
+    codes = wl.codes(bn, rows, seed=31)
+    prog = engine.Program(plan)
+    prog.set_graph(False)
+    roles = prog.step_roles()
+    kinds = np.array([st.kind for st in plan.steps])
+    assert (roles[kinds == planner.KIND_FLAT] == 0).all() and (roles[kinds == planner.KIND_BATCHED] > 0).all()
+    assert (roles == 2).sum() == (roles == 3).sum() >= 8 and (roles == 4).sum() == (roles == 5).sum() == 1
+    firsts = np.flatnonzero((roles == 2) | (roles == 4))
+    launched = np.flatnonzero(roles > 0)
+    for i in firsts:  # the second step of a fused launch is the next launched step
+        nxt = launched[np.searchsorted(launched, i) + 1]
+        assert roles[nxt] == roles[i] + 1
+    assert prog.info()["pairs"] == len(firsts)
+    fused = prog.run(codes, rows).copy()
+    before = prog.info()["launches"]
+    prog.run(codes, rows)
+    n_fused = prog.info()["launches"] - before
+
+    monkeypatch.setenv("SOROBN_B200_PAIR_IDX_LIMIT", "1000")
+    assert set(prog.step_roles().tolist()) == {0, 1}
+    before = prog.info()["launches"]
+    single = prog.run(codes, rows).copy()
+    n_single = prog.info()["launches"] - before
+    assert n_single == n_fused + len(firsts)
+    monkeypatch.delenv("SOROBN_B200_PAIR_IDX_LIMIT")
+    prog.set_tiled(10)
+    assert np.array_equal(single, prog.run(codes, rows))
+    assert np.allclose(fused, single, rtol=3e-6, atol=1e-30)
