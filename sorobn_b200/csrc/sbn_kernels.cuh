@@ -123,6 +123,12 @@ __device__ __forceinline__ void sbn_mbar_wait(uint64_t *bar, uint32_t phase) {
 // Programmatic dependent launch (opt-in on the host side): let the next kernel of the stream
 // be scheduled as soon as every CTA of this one has started, and do not touch anything a
 // predecessor wrote before it has completed.  Both are no-ops for a plain launch.
+// Split form: a kernel whose prologue reads only data no launch of the run writes (CPTs, tables computed at
+// program creation, tile tables, evidence codes) signals its dependents first, does that prologue -- table staging,
+// evidence offsets -- while its predecessor drains, and waits just before it touches a batched factor.
+__device__ __forceinline__ void sbn_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void sbn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void sbn_pdl_entry() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA 
     static_assert(!MX || (CX > 0 && !SLAB), "MX: several eliminated variables on the preload schedule");
     extern __shared__ __align__(16) float s_tab[];
     __shared__ __align__(8) uint64_t s_bar;
-    sbn_pdl_entry();
+    sbn_pdl_launch_dependents();
 
     // Tile chunks vary fastest: the CTAs resident at any moment then cover all tiles of a
     // few row blocks, so operands shared between tiles are re-read from L2, not from HBM.
@@ -510,6 +516,9 @@ __global__ void __launch_bounds__(SBN_TILED_THREADS, (CX > 0 ? ((MX && (NU + NA 
 
     if (staged) sbn_mbar_wait(&s_bar, 0);
     if (!live) return;
+    // everything above read tables, tile tables and evidence codes only; the batched operands below were written
+    // by earlier launches of this run
+    sbn_pdl_wait();
 
     const int ld = static_cast<int>(p.ld);
     const int c0 = p.n_axes > 0 ? p.card[0] : 1;

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, (M1 >= SBN_PAIR_GB ? 4 : 5
     constexpr int T = SBN_PAIR_T, V = kV;
     extern __shared__ __align__(16) float s_canon[];
     __shared__ __align__(8) uint64_t s_bar;
-    sbn_pdl_entry();
+    sbn_pdl_launch_dependents();
 
     const int rblock = blockIdx.x / p.n_chunks;
     const int chunk = blockIdx.x % p.n_chunks;
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(SBN_PAIR_ROWS / kV, (M1 >= SBN_PAIR_GB ? 4 : 5
     }
     sbn_mbar_wait(&s_bar, 0);
     if (!live) return;
+    sbn_pdl_wait();  // coefficients and evidence codes are not written by any launch of the run; F (and G) below are
 
     // element offsets fit 32 bits (sbn_pair_fits): strides are scaled by the row pitch once, an access then costs
     // one IADD3 and one IMAD.WIDE.U32
