@@ -401,3 +401,27 @@ def test_slots_and_order_allow_two_steps_per_launch():
             big = sizes.index(3125)
             consumer = batched[big + 1]
             assert any(f.is_slot and f.batched and f.buf == batched[big].out_slot for f, _, _ in consumer.inputs)
+
+
+@pytest.mark.parametrize("big_last,dfs", [("0", "1"), ("1", "0"), ("0", "0")])
+def test_launch_order_switches_keep_the_answers(monkeypatch, big_last, dfs):
+    """SOROBN_B200_BIG_LAST / SOROBN_B200_DFS only re-order the launches (any topological order of the
+    step tree is valid): same posteriors as the oracle, slot guarantees intact."""
+    monkeypatch.setenv("SOROBN_B200_BIG_LAST", big_last)
+    monkeypatch.setenv("SOROBN_B200_DFS", dfs)
+    for trial in range(40, 46):
+        rng = np.random.default_rng(trial)
+        n = int(rng.integers(6, 13))
+        spec = synthetic.random_dag(n, 3, int(rng.integers(2, 5)), seed=trial)
+        bn = synthetic.load(spec, BayesNet)
+        perm = rng.permutation(n)
+        query = [spec.nodes[perm[0]]]
+        evs = [spec.nodes[i] for i in perm[1:1 + int(rng.integers(1, n - 2))]]
+        events = synthetic.random_events(spec, evs, 5, seed=trial)
+        codes = np.stack([events[v].to_numpy().astype(np.uint8) for v in evs])
+        plan, got = run_plan(bn, query, evs, codes, planner.MODE_BATCHED)
+        assert np.allclose(got, oracle_rows(bn, query, evs, codes), rtol=1e-12, atol=0)
+        batched = [st for st in plan.steps if st.kind == planner.KIND_BATCHED]
+        for prev, st in zip(batched, batched[1:]):
+            held = {f.buf for f, _, _ in prev.inputs if f.is_slot and f.batched}
+            assert st.out_slot not in held
