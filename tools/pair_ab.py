@@ -1,5 +1,6 @@
-"""A/B of the paired-step kernel (csrc/sbn_pair.cu) against one launch per step on one workload.
-   python tools/pair_ab.py grid10x10 [rows]"""
+"""A/B of the fused launches (csrc/sbn_pair.cu: a step and its consumer as one kernel) against one launch per
+step on one workload, device-resident codes, CUDA-event timing of 10 replays after 3 warm-ups.
+   python tools/pair_ab.py grid10x10 [rows]            PAIR_STEPS=1: also print the per-step profile of both"""
 import os
 import sys
 
@@ -38,7 +39,7 @@ for mode, label in ((11, "paired"), (10, "single")):
 d = np.abs(res["paired"] - res["single"]) / np.maximum(res["single"], 1e-30)
 print("max rel diff paired vs single", float(d.max()), "finite", bool(np.isfinite(res["paired"]).all()))
 if os.environ.get("PAIR_STEPS"):
-    # per-step device times (plain launches): pairs show up as (time, 0) on their two steps
+    # per-step device times (plain launches): a fused launch shows up as (time, ~0) on its two steps
     for mode, label in ((11, "paired"), (10, "single")):
         prog.set_tiled(mode)
         ms = prog.profile(d_ev.data_ptr(), rows, rows, d_out.data_ptr(), rows, stream)
